@@ -1,0 +1,210 @@
+/*
+ * xrnerf_b200 — C ABI of the B200-native volumetric-rendering hot path.
+ *
+ * Drop-in boundary for the two native interfaces the reference's hot path binds:
+ *   #1 `raymarch_cuda`  (pybind module; /root/reference/extensions/ngp_raymarch/include/pybind_api.h:3-95,
+ *                        exported in src/pybind_api.cu:6-17) — 10 functions, mirrored 1:1 below (xrb_rm_*);
+ *   #2 `tinycudann`     (third-party; call sites /root/reference/xrnerf/models/mlps/hashnerf_mlp.py:36-45,
+ *                        :55-79, :107-111) — hash-grid / SH encodings and fully-fused MLPs (xrb_tcnn_*, xrb_ngp_*);
+ * plus the fused kernels that replace whole call chains of the reference's Python hot loop
+ * (SURVEY §3b/§3c): xrb_ngp_render_* and the NeRF/Mip-NeRF kernels xrb_nerf_*.
+ *
+ * Conventions (differences from the reference ABI are deliberate and listed in INTEGRATION.md):
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - every entry point takes the CUDA stream to launch on (`void *stream` = cudaStream_t) and NEVER
+ *     synchronises the device (the reference ends every wrapper with cudaDeviceSynchronize());
+ *   - every entry point returns 0 on success, a cudaError_t value (>0) on a CUDA failure, or a negative
+ *     XRB_E_* code on bad arguments (the reference surfaces no errors at all);
+ *   - the hidden per-translation-unit host RNG of the reference (`static pcg32 rng{9121}`, advanced by 2^32
+ *     per API call; raymarch_shared.h:38) is an explicit (seed, n_prior_calls) argument pair;
+ *   - sample buffers are laid out in RAY ORDER (exclusive prefix sums) instead of atomic-arrival order; the
+ *     (count, base) contract of `numsteps` is unchanged.
+ */
+#ifndef XRNERF_B200_H
+#define XRNERF_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XRB_OK 0
+#define XRB_E_BADARG (-1)
+#define XRB_E_UNSUPPORTED (-2)
+#define XRB_E_WORKSPACE (-3)
+
+/* activation enum of the reference (raymarch_shared.h:619-625) */
+#define XRB_ACT_NONE 0
+#define XRB_ACT_RELU 1
+#define XRB_ACT_LOGISTIC 2
+#define XRB_ACT_EXPONENTIAL 3
+
+/* ABI version, bumped on any signature change; and the compute capability the library was built for (100). */
+int xrb_abi_version(void);
+int xrb_built_for_sm(void);
+/* last error string of the calling thread (static storage) */
+const char *xrb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Boundary #1 — raymarch_cuda equivalents
+ * ---------------------------------------------------------------------------------------------- */
+
+/* replaces generate_grid_samples_nerf_nonuniform_api (pybind_api.h:5-10; src/generate_grid_samples_nerf_nonuniform.cu:44-87).
+ * grid f32[8*128^3]; positions f32[n,3]; indices i32[n]. */
+int xrb_rm_generate_grid_samples(const float *grid, int ema_step, int n_elements, int max_cascade, float thresh, float aabb0,
+                                 float aabb1, uint64_t seed, int64_t n_prior_calls, float *positions, int32_t *indices, void *stream);
+
+/* replaces mark_untrained_density_grid_api (pybind_api.h:12-16; src/mark_untrained_density_grid.cu:53-82).
+ * focal f32[I,2]; xforms f32[I,4,3]; grid f32[n_elements] is FULLY written (0 seen / -1 unseen): the reference's
+ * dependence on uninitialised memory is removed. */
+int xrb_rm_mark_untrained_density_grid(const float *focal, const float *xforms, int n_elements, int n_images, int res0, int res1,
+                                       float *grid, void *stream);
+
+/* replaces splat_grid_samples_nerf_max_nearest_neighbor_api (pybind_api.h:18-20). mlp_out f32[n,padded_width]. */
+int xrb_rm_splat_grid_samples(const float *mlp_out, const int32_t *indices, int padded_width, int n, float *grid_tmp, void *stream);
+
+/* replaces ema_grid_samples_nerf_api (pybind_api.h:22-23). */
+int xrb_rm_ema_grid_samples(const float *grid_tmp, int n_elements, float decay, float *grid, void *stream);
+
+/* replaces update_bitfield_api (pybind_api.h:25-26; src/update_bitfield.cu:74-116). mean f32[>=1] (only [0] written);
+ * bitfield u8[8*128^3/8]. Deterministic (fixed-order) mean. */
+int xrb_rm_update_bitfield(const float *grid, float *mean, uint8_t *bitfield, void *stream);
+
+/* replaces rays_sampler_api (pybind_api.h:28-42; src/ray_sampler.cu:118-200).
+ * rays_o/rays_d f32[N,3]; bitfield u8[2097152]; coords_out f32[max_samples,7] (rows = pos_warped[3], dt_warped,
+ * dir_warped[3]); rays_index i32[N]; numsteps i32[N,2] = (count, base); counters i32[2] = (#rays that got a slot,
+ * total samples incl. overflowed rays). metadata/img_ids/xforms are accepted for signature parity and unused,
+ * exactly like the reference kernel (ray_sampler.cu:29-38 reads them into dead locals); they may be NULL.
+ * workspace: device scratch of xrb_rm_rays_sampler_workspace(N) bytes. */
+size_t xrb_rm_rays_sampler_workspace(int n_rays);
+int xrb_rm_rays_sampler(const float *rays_o, const float *rays_d, const uint8_t *bitfield, const float *metadata,
+                        const int32_t *img_ids, const float *xforms, int n_rays, int max_samples, float aabb0, float aabb1,
+                        float near_distance, float cone_angle, uint64_t seed, int64_t n_prior_calls, float *coords_out,
+                        int32_t *rays_index, int32_t *numsteps, int32_t *counters, void *workspace, void *stream);
+
+/* replaces compacted_coord_api (pybind_api.h:44-58; src/compacted_coord.cu:79-143). network_output and the
+ * activations are accepted and unused (the reference's transmittance loop is dead code, Q3). */
+size_t xrb_rm_compacted_coord_workspace(int n_rays);
+int xrb_rm_compacted_coord(const float *network_output, const float *coords_in, const int32_t *numsteps, int n_rays,
+                           int max_compacted, float *coords_out, int32_t *numsteps_compacted, int32_t *ray_counter,
+                           int32_t *step_counter, void *workspace, void *stream);
+
+/* replaces calc_rgb_forward_api (pybind_api.h:60-72). raw f32[S,4]; coords f32[S,7]; bg f32[N,3]; rgb f32[N,3]. */
+int xrb_rm_calc_rgb_forward(const float *raw, const float *coords, const int32_t *numsteps, const int32_t *numsteps_compacted,
+                            const float *bg, int n_rays, int rgb_act, int dens_act, float *rgb_out, void *stream);
+
+/* replaces calc_rgb_backward_api (pybind_api.h:74-86). Writes dL/draw f32[S,4] for the rows owned by rays; the caller
+ * zero-fills padding rows (as the reference's Python wrapper does, hashnerf_render.py:122-125). */
+int xrb_rm_calc_rgb_backward(const float *raw, const int32_t *numsteps_compacted, const float *coords, const float *grad_rgb,
+                             const float *rgb, const float *grid_mean, int n_rays, int rgb_act, int dens_act, float *dl_draw,
+                             void *stream);
+
+/* replaces calc_rgb_influence_api (pybind_api.h:88-95). bg3_host: 3 floats on the HOST (as in the reference). */
+int xrb_rm_calc_rgb_inference(const float *raw, const float *coords, const int32_t *numsteps, const float *bg3_host, int n_rays,
+                              int rgb_act, int dens_act, float *rgb_out, float *alpha_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Boundary #2 — tcnn-shaped encodings / networks, and the fused NGP field
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct {
+    int n_levels;            /* 16 */
+    int n_features;          /* 2 (only 2 is implemented) */
+    int log2_hashmap_size;   /* 19 */
+    int base_resolution;     /* 16 */
+    float per_level_scale;   /* 2^(log2(2048/16)/15), hashnerf_mlp.py:17-20 */
+    int width;               /* n_neurons, 64 (only 64 is implemented) */
+    int density_hidden;      /* hidden layers of density_net (config key num_layers / n_hidden_layers), 1..4 */
+    int color_hidden;        /* hidden layers of color_net, 1..4 */
+} xrb_ngp_config;
+
+/* number of scalars in the hash table / density net / colour net parameter vectors, and level offsets */
+int64_t xrb_tcnn_hashgrid_num_params(const xrb_ngp_config *cfg);
+int64_t xrb_tcnn_density_num_params(const xrb_ngp_config *cfg);
+int64_t xrb_tcnn_color_num_params(const xrb_ngp_config *cfg);
+int xrb_tcnn_hashgrid_layout(const xrb_ngp_config *cfg, uint32_t *offsets_host /*[n_levels+1]*/, float *scales_host, uint32_t *res_host);
+
+/* fp32 master -> fp16 working copy (what tcnn does on every forward; done once per optimiser step here) */
+int xrb_tcnn_cast_params(const float *src, void *dst_fp16, int64_t n, void *stream);
+/* packs the density+colour weights (fp32 master, tcnn layout W[out][in]) into the UMMA shared-memory image
+ * (128-byte-swizzled K-major tiles) the tcgen05 kernels bulk-copy; image size = xrb_ngp_weight_image_bytes(). */
+size_t xrb_ngp_weight_image_bytes(const xrb_ngp_config *cfg);
+int xrb_ngp_pack_weights(const xrb_ngp_config *cfg, const float *density_params, const float *color_params, void *image, void *stream);
+
+/* tcnn.Encoding(HashGrid).forward: x f32[n,3] in [0,1] -> enc fp16[n, n_levels*n_features] */
+int xrb_tcnn_hashgrid_forward(const xrb_ngp_config *cfg, const void *table_fp16, const float *x, int x_stride, int n, void *enc_fp16, void *stream);
+/* tcnn.Encoding(SphericalHarmonics, degree 4).forward: dirs f32[n,3] in [0,1] -> fp16[n,16] */
+int xrb_tcnn_sh4_forward(const float *dirs, int dir_stride, int n, void *out_fp16, void *stream);
+/* tcnn.Network(FullyFusedMLP).forward, SIMT reference-grade implementation: x fp16[n,in_w] -> y fp16[n,16] */
+int xrb_tcnn_mlp_forward(const void *params_fp16, const void *x_fp16, int n, int in_w, int width, int n_hidden, void *y_fp16, void *stream);
+
+/* HashNerfMLP.run_mlp (hashnerf_mlp.py:55-79) fused: pts/dirs f32 rows (stride in floats, so `coords[:, :3]` /
+ * `coords[:, 4:]` views of a [S,7] buffer work in place) -> raw f32[n,4] = (rgb3, density1).
+ * impl: 0 = SIMT (CUDA cores), 1 = tcgen05 tensor-core tiles (weights from `weight_image`). */
+int xrb_ngp_mlp_forward(const xrb_ngp_config *cfg, const void *table_fp16, const void *density_fp16, const void *color_fp16,
+                        const void *weight_image, const float *pts, int pts_stride, const float *dirs, int dirs_stride, int n,
+                        float *raw, int impl, void *stream);
+/* HashNerfMLP.run_density (hashnerf_mlp.py:107-111): -> density f32[n] (raw, pre-activation) */
+int xrb_ngp_density_forward(const xrb_ngp_config *cfg, const void *table_fp16, const void *density_fp16, const void *weight_image,
+                            const float *pts, int pts_stride, int n, float *density, int impl, void *stream);
+
+/* Backward of run_mlp: dL/draw f32[n,4] -> fp32 gradients of the three parameter vectors (ACCUMULATED into the
+ * outputs with atomics; caller zeroes them). */
+int xrb_ngp_mlp_backward(const xrb_ngp_config *cfg, const void *table_fp16, const void *density_fp16, const void *color_fp16,
+                         const float *pts, int pts_stride, const float *dirs, int dirs_stride, const float *dl_draw, int n,
+                         float *d_table, float *d_density, float *d_color, void *stream);
+
+/* Fused Adam step on an fp32 master vector + refresh of its fp16 working copy (torch.optim.Adam semantics with
+ * L2 weight_decay folded into the gradient; configs/instant_ngp/nerf_blender_local01.py:13-18). grad is divided by
+ * grad_div first (world size after a sum all-reduce). */
+int xrb_adam_step(float *param, void *param_fp16, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_div, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused render of a ray batch (inference): replaces the chain
+ *   rays_sampler -> HashNerfMLP.run_mlp -> calc_rgb_influence  (ngp_grid_sampler.py:205-228, hashnerf_mlp.py:55-79,
+ *   hashnerf_render.py:42-46) without materialising coords[S,7] or raw[S,4] in HBM.
+ * rays_o/rays_d f32[N,3]; rgb f32[N,3]; alpha f32[N]; numsteps i32[N,2] (count, base) is also produced;
+ * counters i32[2] as in xrb_rm_rays_sampler (counters[1] = total samples marched).
+ * workspace: xrb_ngp_render_workspace(N, max_samples) bytes.
+ * ---------------------------------------------------------------------------------------------- */
+size_t xrb_ngp_render_workspace(int n_rays, int max_samples);
+int xrb_ngp_render(const xrb_ngp_config *cfg, const void *table_fp16, const void *weight_image, const uint8_t *bitfield,
+                   const float *rays_o, const float *rays_d, int n_rays, int max_samples, float aabb0, float aabb1,
+                   float near_distance, float cone_angle, uint64_t seed, int64_t n_prior_calls, const float *bg3_host, int rgb_act,
+                   int dens_act, float *rgb_out, float *alpha_out, int32_t *numsteps, int32_t *counters, void *workspace,
+                   void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * NeRF / Mip-NeRF composite + sampling kernels (pure-PyTorch in the reference)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* NerfRender.forward (nerf_render.py:47-98) / MipNerfRender (mipnerf_render.py:13-33), forward.
+ * raw f32[N,S,4]; z_vals f32[N,S] (mip==0) or f32[N,S+1] (mip==1); rays_d f32[N,3].
+ * density_act: XRB_ACT_RELU or 4 (= softplus). Outputs rgb[N,3], disp[N], acc[N], weights[N,S]. */
+#define XRB_ACT_SOFTPLUS 4
+int xrb_nerf_composite_forward(const float *raw, const float *z_vals, const float *rays_d, int n_rays, int n_samples, int mip,
+                               int white_bkgd, float rgb_padding, float density_bias, int density_act, float *rgb, float *disp,
+                               float *acc, float *weights, void *stream);
+/* backward wrt raw of rgb (grad_rgb f32[N,3]); disp/acc/weights are treated as non-differentiated outputs
+ * exactly as the reference's losses use them (nerf.py:79-84: loss on rgb only). */
+int xrb_nerf_composite_backward(const float *raw, const float *z_vals, const float *rays_d, const float *grad_rgb, int n_rays,
+                                int n_samples, int mip, int white_bkgd, float rgb_padding, float density_bias, int density_act,
+                                float *d_raw, void *stream);
+
+/* sample_pdf (hierarchical_sample.py:6-53), deterministic (`det`) or with caller-supplied uniforms u f32[N,n_importance].
+ * z_vals f32[N,S], weights f32[N,S] -> z_out f32[N,S+n_importance] sorted, pts f32[N,S+n_importance,3] (may be NULL). */
+int xrb_nerf_sample_pdf(const float *z_vals, const float *weights, const float *rays_o, const float *rays_d, const float *u,
+                        int n_rays, int n_samples, int n_importance, float *z_out, float *pts_out, void *stream);
+
+/* BaseEmbedder.forward (embedders/base.py:57-74): pts f32[M,3], dirs f32[R,3] broadcast over S=M/R samples ->
+ * embedded f32[M, 3+6*multires + 3+6*multires_dirs] */
+int xrb_nerf_posenc(const float *pts, const float *viewdirs, int64_t n_pts, int samples_per_ray, int multires, int multires_dirs,
+                    float *embedded, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XRNERF_B200_H */

@@ -1,0 +1,109 @@
+"""GPU parity of the tcnn-shaped boundary and of the fused HashNerfMLP field (CUDA-core impl 0 and tcgen05 impl 1) against
+oracle/tcnn_oracle.c. Tolerances (stated, fp16 pipeline): encodings 1 fp16 ulp of the value range (2e-7 abs on 1e-4-scale
+table entries), MLP outputs 2e-3 abs / 1e-2 rel (fp16 activations; accumulation order differs on tensor cores)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope='module')
+def field_and_weights():
+    from xrnerf_b200 import synth
+    from xrnerf_b200.ngp import NgpField
+    f = NgpField().cuda()
+    # larger-than-default table values so the hash encoding actually matters in the outputs
+    table, dens, color = synth.ngp_weights(seed=0, hash_range=0.5)
+    with torch.no_grad():
+        f.hash_params.copy_(dev(table)); f.density_params.copy_(dev(dens)); f.color_params.copy_(dev(color))
+    return f, table, dens, color
+
+
+def _pts(n, seed=0):
+    rng = np.random.default_rng(seed)
+    pts = rng.random((n, 3)).astype(np.float32)
+    pts[0] = 0.0; pts[1] = 1.0; pts[2] = [0.0, 1.0, 0.5]
+    dirs = rng.random((n, 3)).astype(np.float32)
+    return pts, dirs
+
+
+def test_layout_matches_oracle(port, field_and_weights):
+    import ctypes as C
+    from xrnerf_b200 import _C
+    f = field_and_weights[0]
+    n, off, sc, res = port.hashgrid_layout()
+    assert n == f.hash_params.numel() == 12196240
+    o2 = (C.c_uint32 * 17)(); s2 = (C.c_float * 16)(); r2 = (C.c_uint32 * 16)()
+    _C.check(_C.lib.xrb_tcnn_hashgrid_layout(f.cfg, o2, s2, r2))
+    assert list(o2) == off.tolist() and list(r2) == res.tolist() and np.array_equal(np.array(list(s2), np.float32), sc)
+
+
+def test_hashgrid_sh_mlp_modules(port, field_and_weights):
+    import xrnerf_b200.tcnn as tcnn
+    from xrnerf_b200.ngp import PER_LEVEL_SCALE
+    f, table, dens, color = field_and_weights
+    pts, dirs = _pts(5000)
+    enc = tcnn.Encoding(3, dict(otype='HashGrid', n_levels=16, n_features_per_level=2, log2_hashmap_size=19, base_resolution=16, per_level_scale=PER_LEVEL_SCALE)).cuda()
+    with torch.no_grad():
+        enc.params.copy_(dev(table))
+    e_gpu = enc(dev(pts)).float().cpu().numpy()
+    e_ref = port.hashgrid_forward(table, pts)
+    assert e_gpu.shape == (5000, 32)
+    assert np.abs(e_gpu - e_ref).max() <= 5e-4  # values up to 0.5 in fp16: 1 ulp = 2.4e-4
+    sh = tcnn.Encoding(3, dict(otype='SphericalHarmonics', degree=4)).cuda()
+    s_gpu = sh(dev(dirs)).float().cpu().numpy()
+    assert np.abs(s_gpu - port.sh4(dirs)).max() <= 2e-3
+    net = tcnn.Network(32, 16, dict(otype='FullyFusedMLP', activation='ReLU', output_activation='None', n_neurons=64, num_layers=1)).cuda()
+    with torch.no_grad():
+        net.params.copy_(dev(dens))
+    x = e_ref.astype(np.float16)
+    y_gpu = net(dev(x)).float().cpu().numpy()
+    y_ref = port.mlp_forward(dens, x.astype(np.float32), 64, 1)
+    assert np.abs(y_gpu - y_ref).max() <= 2e-3 + 1e-2 * np.abs(y_ref).max()
+
+
+@pytest.mark.parametrize('impl', [0, 1])
+def test_fused_field_vs_oracle(port, field_and_weights, impl):
+    f, table, dens, color = field_and_weights
+    for n in (1, 127, 128, 129, 5000, 40000):
+        pts, dirs = _pts(n, seed=n)
+        raw_ref = port.ngp_mlp_forward(table, dens, color, pts, dirs)
+        raw = f.run_mlp(dev(pts), dev(dirs), impl=impl).cpu().numpy()
+        assert raw.shape == (n, 4)
+        assert np.isfinite(raw).all()
+        err = np.abs(raw - raw_ref).max()
+        assert err <= 2e-3 + 1e-2 * np.abs(raw_ref).max(), (impl, n, err)
+        d_ref = port.ngp_density_forward(table, dens, pts)
+        d = f.run_density(dev(pts), impl=impl).cpu().numpy().reshape(-1)
+        assert np.abs(d - d_ref).max() <= 2e-3 + 1e-2 * np.abs(d_ref).max()
+
+
+def test_fused_field_strided_views_and_impl_agreement(field_and_weights):
+    f = field_and_weights[0]
+    rng = np.random.default_rng(9)
+    coords = dev(rng.random((10000, 7)).astype(np.float32))
+    a = f.run_mlp(coords[:, :3], coords[:, 4:], impl=0)
+    b = f.run_mlp(coords[:, :3], coords[:, 4:], impl=1)
+    c = f.run_mlp(coords[:, :3].contiguous(), coords[:, 4:].contiguous(), impl=1)
+    assert torch.equal(b, c)
+    assert (a - b).abs().max().item() <= 2e-3 + 1e-2 * a.abs().max().item()
+
+
+def test_deeper_networks(port):
+    """n_hidden_layers up to 4 (tcnn's own default is 5 hidden layers when the reference's `num_layers` key is ignored)."""
+    from xrnerf_b200 import synth
+    from xrnerf_b200.ngp import NgpField
+    f = NgpField(density_hidden=2, color_hidden=3).cuda()
+    table, dens, color = synth.ngp_weights(seed=2, dens_hidden=2, color_hidden=3, hash_range=0.5)
+    with torch.no_grad():
+        f.hash_params.copy_(dev(table)); f.density_params.copy_(dev(dens)); f.color_params.copy_(dev(color))
+    pts, dirs = _pts(3000, seed=4)
+    ref = port.ngp_mlp_forward(table, dens, color, pts, dirs, dens_hidden=2, color_hidden=3)
+    for impl in (0, 1):
+        raw = f.run_mlp(dev(pts), dev(dirs), impl=impl).cpu().numpy()
+        assert np.abs(raw - ref).max() <= 3e-3 + 1e-2 * np.abs(ref).max()

@@ -1,0 +1,95 @@
+"""ctypes binding of libxrnerf_b200.so (the C ABI declared in include/xrnerf_b200.h).
+
+The product path has NO CPU fallback: importing this module without the built CUDA library raises, and every call
+checks the status code the library returns. torch is used only for device memory and streams.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libxrnerf_b200.so')
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(f'{LIB_PATH} is missing: run `python -m xrnerf_b200.build` (needs nvcc; cross-compiles for sm_100a without a GPU). '
+                      'xrnerf_b200 has no CPU or PyTorch fallback for its kernels.')
+
+lib = C.CDLL(LIB_PATH)
+
+
+class NgpConfig(C.Structure):
+    _fields_ = [('n_levels', C.c_int), ('n_features', C.c_int), ('log2_hashmap_size', C.c_int), ('base_resolution', C.c_int),
+                ('per_level_scale', C.c_float), ('width', C.c_int), ('density_hidden', C.c_int), ('color_hidden', C.c_int)]
+
+
+P = C.c_void_p
+_i, _f, _u64, _i64, _sz = C.c_int, C.c_float, C.c_uint64, C.c_int64, C.c_size_t
+_cfg = C.POINTER(NgpConfig)
+
+_SIGS = {
+    'xrb_abi_version': (C.c_int, []),
+    'xrb_built_for_sm': (C.c_int, []),
+    'xrb_last_error': (C.c_char_p, []),
+    'xrb_rm_generate_grid_samples': (_i, [P, _i, _i, _i, _f, _f, _f, _u64, _i64, P, P, P]),
+    'xrb_rm_mark_untrained_density_grid': (_i, [P, P, _i, _i, _i, _i, P, P]),
+    'xrb_rm_splat_grid_samples': (_i, [P, P, _i, _i, P, P]),
+    'xrb_rm_ema_grid_samples': (_i, [P, _i, _f, P, P]),
+    'xrb_rm_update_bitfield': (_i, [P, P, P, P]),
+    'xrb_rm_rays_sampler_workspace': (_sz, [_i]),
+    'xrb_rm_rays_sampler': (_i, [P, P, P, P, P, P, _i, _i, _f, _f, _f, _f, _u64, _i64, P, P, P, P, P, P]),
+    'xrb_rm_compacted_coord_workspace': (_sz, [_i]),
+    'xrb_rm_compacted_coord': (_i, [P, P, P, _i, _i, P, P, P, P, P, P]),
+    'xrb_rm_calc_rgb_forward': (_i, [P, P, P, P, P, _i, _i, _i, P, P]),
+    'xrb_rm_calc_rgb_backward': (_i, [P, P, P, P, P, P, _i, _i, _i, P, P]),
+    'xrb_rm_calc_rgb_inference': (_i, [P, P, P, C.POINTER(C.c_float), _i, _i, _i, P, P, P]),
+    'xrb_tcnn_hashgrid_num_params': (_i64, [_cfg]),
+    'xrb_tcnn_density_num_params': (_i64, [_cfg]),
+    'xrb_tcnn_color_num_params': (_i64, [_cfg]),
+    'xrb_tcnn_hashgrid_layout': (_i, [_cfg, P, P, P]),
+    'xrb_tcnn_cast_params': (_i, [P, P, _i64, P]),
+    'xrb_ngp_weight_image_bytes': (_sz, [_cfg]),
+    'xrb_ngp_pack_weights': (_i, [_cfg, P, P, P, P]),
+    'xrb_tcnn_hashgrid_forward': (_i, [_cfg, P, P, _i, _i, P, P]),
+    'xrb_tcnn_sh4_forward': (_i, [P, _i, _i, P, P]),
+    'xrb_tcnn_mlp_forward': (_i, [P, P, _i, _i, _i, _i, P, P]),
+    'xrb_ngp_mlp_forward': (_i, [_cfg, P, P, P, P, P, _i, P, _i, _i, P, _i, P]),
+    'xrb_ngp_density_forward': (_i, [_cfg, P, P, P, P, _i, _i, P, _i, P]),
+    'xrb_ngp_render_workspace': (_sz, [_i, _i]),
+    'xrb_ngp_render': (_i, [_cfg, P, P, P, P, P, _i, _i, _f, _f, _f, _f, _u64, _i64, C.POINTER(C.c_float), _i, _i, P, P, P, P, P, P]),
+}
+
+EXPORTS = sorted(_SIGS)  # every symbol the header declares and the library currently implements
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class XrbError(RuntimeError):
+    pass
+
+
+def check(status, what=''):
+    if status != 0:
+        raise XrbError(f'{what} failed with status {status}: {lib.xrb_last_error().decode()}')
+
+
+def ptr(t):
+    """Device (or host) pointer of a tensor; None -> NULL."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def float3(v):
+    arr = (C.c_float * 3)(*[float(x) for x in v])
+    return arr
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise XrbError('xrnerf_b200 kernels need CUDA tensors; there is no CPU fallback')

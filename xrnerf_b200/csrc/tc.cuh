@@ -1,0 +1,89 @@
+// xrnerf_b200 — thin inline-PTX wrappers for the Blackwell (sm_100a) tensor-core path: tcgen05.mma/ld/alloc/commit,
+// mbarrier, 1-D TMA bulk copy, proxy fences. No CUTLASS dependency; encodings follow cute/arch/mma_sm100_desc.hpp.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace xrb { namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) {} }
+
+// ---- TMA: 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes),
+                 "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- proxy / tcgen05 fences
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t n_threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory"); }
+
+// ---- TMEM allocation (one full warp executes; result lands in shared memory)
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_result) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) { asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory"); }
+
+// ---- descriptors
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B, 8-row atoms 1024 B apart (SBO), version 1 (Blackwell)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr_bytes) {
+    return (uint64_t)((smem_addr_bytes >> 4) & 0x3FFFu) | (1ull << 16) /*LBO (ignored for swizzled K-major)*/ | ((uint64_t)(1024u >> 4) << 32) /*SBO*/ | (1ull << 46) /*version*/ |
+           (2ull << 61) /*SWIZZLE_128B*/;
+}
+// instruction descriptor: D=F32, A=B=F16, both K-major, M=128, N given
+__host__ __device__ constexpr uint32_t idesc_f16_m128(uint32_t n) { return (1u << 4) | (0u << 7) | (0u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; single-thread issue
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// all previously issued tcgen05 async ops of this thread arrive on the mbarrier when done (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t *bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+
+// ---- TMEM -> registers: lane = this thread's row, N consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 32 columns; the wait is inside the same asm statement so the compiler cannot hoist uses of r[] above it
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+
+}}  // namespace xrb::tc
