@@ -177,6 +177,9 @@ int xrb_ngp_render(const xrb_ngp_config *cfg, const void *table_fp16, const void
                    int dens_act, float *rgb_out, float *alpha_out, int32_t *numsteps, int32_t *counters, void *workspace,
                    void *stream);
 
+/* measurement hook: cudaEvent_t handles recorded right before / after the field kernel inside xrb_ngp_render (NULL disables) */
+int xrb_ngp_render_set_profile_events(void *before_field, void *after_field);
+
 /* ------------------------------------------------------------------------------------------------
  * NeRF / Mip-NeRF composite + sampling kernels (pure-PyTorch in the reference)
  * ---------------------------------------------------------------------------------------------- */

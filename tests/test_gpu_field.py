@@ -27,7 +27,8 @@ def field_and_weights():
 def _pts(n, seed=0):
     rng = np.random.default_rng(seed)
     pts = rng.random((n, 3)).astype(np.float32)
-    pts[0] = 0.0; pts[1] = 1.0; pts[2] = [0.0, 1.0, 0.5]
+    if n >= 3:
+        pts[0] = 0.0; pts[1] = 1.0; pts[2] = [0.0, 1.0, 0.5]
     dirs = rng.random((n, 3)).astype(np.float32)
     return pts, dirs
 

@@ -1,0 +1,259 @@
+// xrnerf_b200 — NeRF / Mip-NeRF per-ray kernels that are pure PyTorch in the reference (≈25 tiny ATen kernels per
+// render call, a full sort + expanded gathers per sample_pdf call): one launch each, one WARP per ray,
+// lanes over samples with shuffle scans. References relative to /root/reference/xrnerf/models/.
+#include "common.cuh"
+
+namespace xrb {
+
+__device__ __forceinline__ float wincl_sum(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { float n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += n; }
+    return v;
+}
+__device__ __forceinline__ float wincl_prod(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { float n = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v *= n; }
+    return v;
+}
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // F.softplus(beta=1, threshold=20)
+
+struct CompositeParams { int n_rays, n_samples, mip, white_bkgd, density_act; float rgb_padding, density_bias; };
+
+// per-sample quantities of renders/nerf_render.py:61-83 (and mipnerf_render.py:27-33 when mip)
+__device__ __forceinline__ void sample_terms(const CompositeParams &p, const float *__restrict__ raw, const float *__restrict__ z, float dnorm, int k, float4 &r, float &sd,
+                                             float &alpha) {
+    r = __ldg(reinterpret_cast<const float4 *>(raw) + k);
+    float dist = p.mip ? (z[k + 1] - z[k]) : (k + 1 < p.n_samples ? z[k + 1] - z[k] : 1e10f);
+    dist *= dnorm;
+    float a = r.w + p.density_bias;
+    float dens = p.density_act == XRB_ACT_SOFTPLUS ? softplusf_(a) : fmaxf(a, 0.f);
+    sd = dens * dist;
+    alpha = 1.f - expf(-sd);
+}
+
+// BACKWARD == false: rgb/disp/acc/weights.  BACKWARD == true: d_raw given grad_rgb (loss on rgb only, nerf.py:79-84 / mipnerf.py:49-57)
+template <bool BACKWARD>
+__global__ void __launch_bounds__(256) nerf_composite_kernel(CompositeParams p, const float *__restrict__ raw, const float *__restrict__ z_vals, const float *__restrict__ rays_d,
+                                                             const float *__restrict__ grad_rgb, float *__restrict__ rgb_out, float *__restrict__ disp_out, float *__restrict__ acc_out,
+                                                             float *__restrict__ weights_out, float *__restrict__ d_raw) {
+    const int lane = threadIdx.x & 31;
+    const int ray = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (ray >= p.n_rays) return;
+    const int S = p.n_samples, zs = p.mip ? S + 1 : S;
+    const float *rw = raw + (size_t)ray * S * 4, *z = z_vals + (size_t)ray * zs;
+    const float dx = rays_d[3 * (size_t)ray], dy = rays_d[3 * (size_t)ray + 1], dz = rays_d[3 * (size_t)ray + 2];
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float pad_mul = 1.f + 2.f * p.rgb_padding;
+    float gx = 0, gy = 0, gz = 0;
+    if (BACKWARD) { gx = grad_rgb[3 * (size_t)ray]; gy = grad_rgb[3 * (size_t)ray + 1]; gz = grad_rgb[3 * (size_t)ray + 2]; }
+    // ---- pass 1: forward accumulation
+    float carry = p.mip ? 0.f : 1.f;  // mip: running sum of sigma*delta; nerf: running product of (1-alpha+1e-10)
+    float ax = 0, ay = 0, az = 0, acc = 0, depth = 0, total_wg = 0;
+    for (int k0 = 0; k0 < S; k0 += 32) {
+        int k = k0 + lane; bool valid = k < S;
+        float4 r = make_float4(0, 0, 0, 0); float sd = 0, alpha = 0;
+        if (valid) sample_terms(p, rw, z, dnorm, k, r, sd, alpha);
+        float T;
+        if (p.mip) { float inc = wincl_sum(sd, lane); T = expf(-(carry + inc - sd)); carry += __shfl_sync(0xffffffffu, inc, 31); }
+        else { float f = valid ? (1.f - alpha + 1e-10f) : 1.f; float inc = wincl_prod(f, lane); float ex = __shfl_up_sync(0xffffffffu, inc, 1); T = carry * (lane == 0 ? 1.f : ex); carry *= __shfl_sync(0xffffffffu, inc, 31); }
+        float w = valid ? alpha * T : 0.f;
+        float cx = sigmoidf_(r.x) * pad_mul - p.rgb_padding, cy = sigmoidf_(r.y) * pad_mul - p.rgb_padding, cz = sigmoidf_(r.z) * pad_mul - p.rgb_padding;
+        if (!BACKWARD) {
+            ax += w * cx; ay += w * cy; az += w * cz; acc += w;
+            if (valid) { depth += w * (p.mip ? 0.5f * (z[k] + z[k + 1]) : z[k]); weights_out[(size_t)ray * S + k] = w; }
+        } else {
+            float wb = p.white_bkgd ? 1.f : 0.f;
+            total_wg += w * (gx * (cx - wb) + gy * (cy - wb) + gz * (cz - wb));
+        }
+    }
+    if (!BACKWARD) {
+        ax = wsum(ax); ay = wsum(ay); az = wsum(az); acc = wsum(acc); depth = wsum(depth);
+        if (lane == 0) {
+            if (p.white_bkgd) { ax += 1.f - acc; ay += 1.f - acc; az += 1.f - acc; }
+            rgb_out[3 * (size_t)ray] = ax; rgb_out[3 * (size_t)ray + 1] = ay; rgb_out[3 * (size_t)ray + 2] = az;
+            acc_out[ray] = acc;
+            float q = depth / acc, disp;
+            if (p.mip) { if (isnan(q)) q = INFINITY; disp = fmaxf(fminf(q, z[S]), z[0]); }          // mipnerf_render.py:18-24
+            else disp = 1.f / fmaxf(1e-10f, q);                                                       // nerf_render.py:32-36 (torch.max propagates NaN)
+            if (!p.mip && isnan(q)) disp = q;
+            disp_out[ray] = disp;
+        }
+        return;
+    }
+    // ---- pass 2 (backward): dL/d(sigma*delta_i) needs the suffix sum of w_k*G_k over k > i
+    total_wg = wsum(total_wg);
+    carry = p.mip ? 0.f : 1.f;
+    float prefix_wg = 0.f;
+    for (int k0 = 0; k0 < S; k0 += 32) {
+        int k = k0 + lane; bool valid = k < S;
+        float4 r = make_float4(0, 0, 0, 0); float sd = 0, alpha = 0;
+        if (valid) sample_terms(p, rw, z, dnorm, k, r, sd, alpha);
+        float T;
+        if (p.mip) { float inc = wincl_sum(sd, lane); T = expf(-(carry + inc - sd)); carry += __shfl_sync(0xffffffffu, inc, 31); }
+        else { float f = valid ? (1.f - alpha + 1e-10f) : 1.f; float inc = wincl_prod(f, lane); float ex = __shfl_up_sync(0xffffffffu, inc, 1); T = carry * (lane == 0 ? 1.f : ex); carry *= __shfl_sync(0xffffffffu, inc, 31); }
+        float w = valid ? alpha * T : 0.f;
+        float sx = sigmoidf_(r.x), sy = sigmoidf_(r.y), sz = sigmoidf_(r.z);
+        float cx = sx * pad_mul - p.rgb_padding, cy = sy * pad_mul - p.rgb_padding, cz = sz * pad_mul - p.rgb_padding;
+        float wb = p.white_bkgd ? 1.f : 0.f;
+        float G = gx * (cx - wb) + gy * (cy - wb) + gz * (cz - wb);
+        float inc_wg = wincl_sum(w * G, lane);
+        float suffix = total_wg - (prefix_wg + inc_wg);
+        prefix_wg += __shfl_sync(0xffffffffu, inc_wg, 31);
+        if (valid) {
+            float one_m = 1.f - alpha;
+            float dL_dsd = p.mip ? (one_m * T * G - suffix) : (one_m * (T * G - suffix / (one_m + 1e-10f)));
+            float dist = p.mip ? (z[k + 1] - z[k]) : (k + 1 < S ? z[k + 1] - z[k] : 1e10f);
+            dist *= dnorm;
+            float a = r.w + p.density_bias;
+            float dact = p.density_act == XRB_ACT_SOFTPLUS ? (a > 20.f ? 1.f : sigmoidf_(a)) : (a > 0.f ? 1.f : 0.f);
+            float4 o;
+            o.x = gx * w * sx * (1.f - sx) * pad_mul; o.y = gy * w * sy * (1.f - sy) * pad_mul; o.z = gz * w * sz * (1.f - sz) * pad_mul;
+            o.w = dL_dsd * dist * dact;
+            reinterpret_cast<float4 *>(d_raw)[(size_t)ray * S + k] = o;
+        }
+    }
+}
+
+// sample_pdf (networks/utils/hierarchical_sample.py:6-53): one warp per ray, everything in shared memory, bitonic merge sort
+constexpr int PDF_WARPS = 4;
+constexpr int PDF_MAX_S = 256;   // coarse samples
+constexpr int PDF_MAX_OUT = 512; // coarse + importance
+__global__ void __launch_bounds__(PDF_WARPS * 32) sample_pdf_kernel(int n_rays, int S, int n_imp, const float *__restrict__ z_vals, const float *__restrict__ weights,
+                                                                    const float *__restrict__ rays_o, const float *__restrict__ rays_d, const float *__restrict__ u_in,
+                                                                    float *__restrict__ z_out, float *__restrict__ pts_out) {
+    __shared__ float s_cdf[PDF_WARPS][PDF_MAX_S];
+    __shared__ float s_bins[PDF_WARPS][PDF_MAX_S];
+    __shared__ float s_z[PDF_WARPS][PDF_MAX_OUT];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ray = blockIdx.x * PDF_WARPS + wid;
+    if (ray >= n_rays) return;
+    const float *z = z_vals + (size_t)ray * S, *w = weights + (size_t)ray * S;
+    float *cdf = s_cdf[wid], *bins = s_bins[wid], *zz = s_z[wid];
+    const int nb = S - 1;   // bins (mid-points): S-1 ; pdf entries: S-2 ; cdf entries: S-1
+    float part = 0.f;
+    for (int k = lane; k < S - 2; k += 32) part += w[k + 1] + 1e-5f;
+    const float wsum_all = wsum(part);
+    for (int k = lane; k < nb; k += 32) bins[k] = 0.5f * (z[k + 1] + z[k]);
+    __syncwarp();
+    if (lane == 0) {  // sequential cumsum like torch.cumsum on the reference's CPU path
+        float c = 0.f; cdf[0] = 0.f;
+        for (int k = 0; k < S - 2; ++k) { c += (w[k + 1] + 1e-5f) / wsum_all; cdf[k + 1] = c; }
+    }
+    __syncwarp();
+    const int ncdf = S - 1;
+    for (int j = lane; j < n_imp; j += 32) {
+        // torch.linspace(0,1,n): step = 1/(n-1); second half computed from the end (ATen's symmetric formulation)
+        float u;
+        if (u_in) u = u_in[(size_t)ray * n_imp + j];
+        else { float step = 1.0f / (float)(n_imp - 1); u = j < n_imp / 2 ? step * (float)j : 1.0f - step * (float)(n_imp - 1 - j); }
+        int lo = 0, hi = ncdf;   // searchsorted(right=True): first index with cdf[idx] > u
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+        int below = max(0, lo - 1), above = min(ncdf - 1, lo);
+        float c0 = cdf[below], c1 = cdf[above], b0 = bins[below], b1 = bins[above];
+        float denom = c1 - c0; if (denom < 1e-5f) denom = 1.f;
+        float t = (u - c0) / denom;
+        zz[S + j] = b0 + t * (b1 - b0);
+    }
+    for (int k = lane; k < S; k += 32) zz[k] = z[k];
+    const int total = S + n_imp;
+    int np2 = 1; while (np2 < total) np2 <<= 1;
+    for (int k = total + lane; k < np2; k += 32) zz[k] = INFINITY;
+    __syncwarp();
+    for (int size = 2; size <= np2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = lane; t < np2 / 2; t += 32) {
+                int i = 2 * t - (t & (stride - 1)), j = i + stride;
+                bool up = ((i & size) == 0);
+                float a = zz[i], b = zz[j];
+                if ((a > b) == up) { zz[i] = b; zz[j] = a; }
+            }
+            __syncwarp();
+        }
+    const float ox = rays_o[3 * (size_t)ray], oy = rays_o[3 * (size_t)ray + 1], oz = rays_o[3 * (size_t)ray + 2];
+    const float dx = rays_d[3 * (size_t)ray], dy = rays_d[3 * (size_t)ray + 1], dz = rays_d[3 * (size_t)ray + 2];
+    for (int k = lane; k < total; k += 32) {
+        float v = zz[k];
+        z_out[(size_t)ray * total + k] = v;
+        if (pts_out) { float *pp = pts_out + ((size_t)ray * total + k) * 3; pp[0] = ox + dx * v; pp[1] = oy + dy * v; pp[2] = oz + dz * v; }
+    }
+}
+
+// BaseEmbedder.forward (embedders/base.py:57-74): one thread per output element (coalesced row writes)
+__global__ void __launch_bounds__(256) posenc_kernel(int64_t n_pts, int samples_per_ray, int multires, int multires_dirs, const float *__restrict__ pts,
+                                                     const float *__restrict__ viewdirs, float *__restrict__ out) {
+    const int c_pts = 3 + 6 * multires, c_dir = 3 + 6 * multires_dirs, C = c_pts + c_dir;
+    const int64_t total = n_pts * C;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = idx / C; int c = (int)(idx - i * C);
+        const float *src; int cc;
+        if (c < c_pts) { src = pts + 3 * i; cc = c; } else { src = viewdirs + 3 * (i / samples_per_ray); cc = c - c_pts; }
+        float v;
+        if (cc < 3) v = src[cc];
+        else { int q = cc - 3, band = q / 6, r = q % 6; float x = src[r % 3] * exp2f((float)band); v = r < 3 ? sinf(x) : cosf(x); }
+        out[idx] = v;
+    }
+}
+
+}  // namespace xrb
+
+using namespace xrb;
+
+extern "C" {
+
+static int composite_args_ok(const float *raw, const float *z, const float *d, int n_rays, int n_samples, int density_act) {
+    if (n_rays < 0 || n_samples < 1) { set_error("nerf_composite: bad size"); return XRB_E_BADARG; }
+    if (!(density_act == XRB_ACT_RELU || density_act == XRB_ACT_SOFTPLUS)) { set_error("nerf_composite: density activation must be relu(1) or softplus(4)"); return XRB_E_UNSUPPORTED; }
+    if (n_rays && (!raw || !z || !d)) { set_error("nerf_composite: null pointer"); return XRB_E_BADARG; }
+    if (((uintptr_t)raw & 15) != 0) { set_error("nerf_composite: raw must be 16-byte aligned"); return XRB_E_BADARG; }
+    return XRB_OK;
+}
+
+int xrb_nerf_composite_forward(const float *raw, const float *z_vals, const float *rays_d, int n_rays, int n_samples, int mip, int white_bkgd, float rgb_padding, float density_bias,
+                               int density_act, float *rgb, float *disp, float *acc, float *weights, void *stream) {
+    int e = composite_args_ok(raw, z_vals, rays_d, n_rays, n_samples, density_act); if (e) return e;
+    if (n_rays == 0) return XRB_OK;
+    XRB_REQUIRE(rgb && disp && acc && weights, "nerf_composite_forward: null output");
+    CompositeParams p{n_rays, n_samples, mip, white_bkgd, density_act, rgb_padding, density_bias};
+    int blocks = (int)(((size_t)n_rays * 32 + 255) / 256);
+    nerf_composite_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, raw, z_vals, rays_d, nullptr, rgb, disp, acc, weights, nullptr);
+    return check_launch("nerf_composite_forward");
+}
+
+int xrb_nerf_composite_backward(const float *raw, const float *z_vals, const float *rays_d, const float *grad_rgb, int n_rays, int n_samples, int mip, int white_bkgd, float rgb_padding,
+                                float density_bias, int density_act, float *d_raw, void *stream) {
+    int e = composite_args_ok(raw, z_vals, rays_d, n_rays, n_samples, density_act); if (e) return e;
+    if (n_rays == 0) return XRB_OK;
+    XRB_REQUIRE(grad_rgb && d_raw && ((uintptr_t)d_raw & 15) == 0, "nerf_composite_backward: null/misaligned pointer");
+    CompositeParams p{n_rays, n_samples, mip, white_bkgd, density_act, rgb_padding, density_bias};
+    int blocks = (int)(((size_t)n_rays * 32 + 255) / 256);
+    nerf_composite_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, raw, z_vals, rays_d, grad_rgb, nullptr, nullptr, nullptr, nullptr, d_raw);
+    return check_launch("nerf_composite_backward");
+}
+
+int xrb_nerf_sample_pdf(const float *z_vals, const float *weights, const float *rays_o, const float *rays_d, const float *u, int n_rays, int n_samples, int n_importance, float *z_out,
+                        float *pts_out, void *stream) {
+    XRB_REQUIRE(n_rays >= 0 && n_samples >= 3 && n_importance >= 2, "sample_pdf: bad size");
+    if (n_samples > PDF_MAX_S || n_samples + n_importance > PDF_MAX_OUT) { set_error("sample_pdf: n_samples<=256 and n_samples+n_importance<=512 supported"); return XRB_E_UNSUPPORTED; }
+    if (n_rays == 0) return XRB_OK;
+    XRB_REQUIRE(z_vals && weights && rays_o && rays_d && z_out, "sample_pdf: null pointer");
+    sample_pdf_kernel<<<(n_rays + PDF_WARPS - 1) / PDF_WARPS, PDF_WARPS * 32, 0, (cudaStream_t)stream>>>(n_rays, n_samples, n_importance, z_vals, weights, rays_o, rays_d, u, z_out, pts_out);
+    return check_launch("sample_pdf");
+}
+
+int xrb_nerf_posenc(const float *pts, const float *viewdirs, int64_t n_pts, int samples_per_ray, int multires, int multires_dirs, float *embedded, void *stream) {
+    XRB_REQUIRE(n_pts >= 0 && samples_per_ray >= 1 && multires >= 0 && multires_dirs >= 0, "posenc: bad size");
+    if (n_pts == 0) return XRB_OK;
+    XRB_REQUIRE(pts && viewdirs && embedded, "posenc: null pointer");
+    int64_t total = n_pts * (6 + 6 * (int64_t)(multires + multires_dirs));
+    int64_t blocks = (total + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
+    posenc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n_pts, samples_per_ray, multires, multires_dirs, pts, viewdirs, embedded);
+    return check_launch("posenc");
+}
+
+}  // extern "C"

@@ -6,7 +6,13 @@
 // the single-launch variant is tracked in DESIGN.md §6.
 #include "ngp_field.cuh"
 
+static thread_local cudaEvent_t g_ev_field0 = nullptr, g_ev_field1 = nullptr;
+
 extern "C" {
+
+// Measurement hook: when set (non-NULL cudaEvent_t handles), xrb_ngp_render records them on its stream immediately before and
+// after the field kernel launch, so a caller can time the dominant kernel live inside its own timed region (bench.py roofline).
+int xrb_ngp_render_set_profile_events(void *before_field, void *after_field) { g_ev_field0 = (cudaEvent_t)before_field; g_ev_field1 = (cudaEvent_t)after_field; return XRB_OK; }
 
 size_t xrb_ngp_render_workspace(int n_rays, int max_samples) {
     size_t a = (xrb_rm_rays_sampler_workspace(n_rays) + 255) & ~(size_t)255;
@@ -31,7 +37,9 @@ int xrb_ngp_render(const xrb_ngp_config *cfg, const void *table_fp16, const void
                             numsteps, counters, ws, stream);
     if (e) return e;
     // counters[1] counts overflowed rays too; rows beyond max_samples do not exist, launch_field clamps to max_samples
+    if (g_ev_field0) cudaEventRecord(g_ev_field0, s);
     e = xrb::launch_field(cfg, table_fp16, nullptr, nullptr, weight_image, coords, 7, coords + 4, 7, max_samples, counters + 1, raw, 1, false, s);
+    if (g_ev_field1) cudaEventRecord(g_ev_field1, s);
     if (e) return e;
     return xrb_rm_calc_rgb_inference(raw, coords, numsteps, bg3_host, n_rays, rgb_act, dens_act, rgb_out, alpha_out, stream);
 }
