@@ -207,6 +207,16 @@ int xrb_nerf_sample_pdf(const float *z_vals, const float *weights, const float *
 int xrb_nerf_posenc(const float *pts, const float *viewdirs, int64_t n_pts, int samples_per_ray, int multires, int multires_dirs,
                     float *embedded, void *stream);
 
+/* Mip-NeRF cast_rays + MipNerfEmbedder.forward (networks/utils/mip.py:66-129, embedders/mipnerf_embedder.py:43-99, cone, diag):
+ * z_vals f32[N,S+1], radii f32[N] -> embedded f32[N*S, 6*(max_deg_point-min_deg_point) + 3 + 6*(max_deg_view-min_deg_view)];
+ * means_out/covs_out f32[N,S,3] optional (both or neither). */
+int xrb_mip_embed(const float *z_vals, const float *rays_o, const float *rays_d, const float *radii, const float *viewdirs, int n_rays, int n_samples, int min_deg_point,
+                  int max_deg_point, int min_deg_view, int max_deg_view, float *embedded, float *means_out, float *covs_out, void *stream);
+
+/* Mip-NeRF resample_along_rays / sorted_piecewise_constant_pdf (networks/utils/mip.py:7-63,:146-176): weights f32[N,S], z_vals f32[N,S+1]
+ * -> z_out f32[N,S+1]; u f32[N,S+1] optional (NULL = the deterministic linspace of randomized=False). */
+int xrb_mip_resample(const float *z_vals, const float *weights, const float *u, int n_rays, int n_samples, float resample_padding, float *z_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,7 +48,7 @@ def test_render_matches_oracle_chain(port, scene, setup):
         assert np.array_equal(ns.cpu().numpy(), ns_ref) and np.array_equal(cnt.cpu().numpy(), cnt_ref)
         assert np.abs(rgb.cpu().numpy() - rgb_ref).max() <= 2e-3
         assert np.abs(alpha.cpu().numpy() - alpha_ref).max() <= 2e-3
-    assert alpha_ref.max() > 0.5  # the scene is actually visible with these weights
+    assert alpha_ref.max() > 0.2  # the scene is actually visible with these weights
 
 
 def test_render_full_image_properties(scene, setup):

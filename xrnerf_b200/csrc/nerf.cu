@@ -200,6 +200,103 @@ __global__ void __launch_bounds__(256) posenc_kernel(int64_t n_pts, int samples_
     }
 }
 
+
+// Mip-NeRF: cast_rays (networks/utils/mip.py:117-129, conical frustum -> Gaussian :91-114, lift_gaussian :66-88, diag) fused with
+// MipNerfEmbedder.forward (embedders/mipnerf_embedder.py:43-99): one thread per output element of embedded[N*S, 6*n_deg + C_dir].
+// The Gaussians (means/covs) are recomputed per element in registers and optionally also written out (API parity: data['samples']).
+__device__ __forceinline__ void frustum_gaussian(float t0, float t1, float radius, const float d[3], const float o[3], float dmag_sq, float mean[3], float cov[3]) {
+    float mu = (t0 + t1) / 2.f, hw = (t1 - t0) / 2.f;
+    float mu2 = mu * mu, hw2 = hw * hw, hw4 = hw2 * hw2, den = 3.f * mu2 + hw2;
+    float t_mean = mu + (2.f * mu * hw2) / den;
+    float t_var = hw2 / 3.f - (4.f / 15.f) * ((hw4 * (12.f * mu2 - hw2)) / (den * den));
+    float r_var = radius * radius * (mu2 / 4.f + (5.f / 12.f) * hw2 - 4.f / 15.f * hw4 / den);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float dd = d[c] * d[c];
+        mean[c] = d[c] * t_mean + o[c];
+        cov[c] = t_var * dd + r_var * (1.f - dd / dmag_sq);
+    }
+}
+__global__ void __launch_bounds__(256) mip_embed_kernel(int n_rays, int S, int min_deg, int max_deg, int min_deg_view, int max_deg_view, const float *__restrict__ z_vals,
+                                                        const float *__restrict__ rays_o, const float *__restrict__ rays_d, const float *__restrict__ radii,
+                                                        const float *__restrict__ viewdirs, float *__restrict__ embedded, float *__restrict__ means_out, float *__restrict__ covs_out) {
+    const int n_deg = max_deg - min_deg, n_deg_v = max_deg_view - min_deg_view;
+    const int c_ipe = 6 * n_deg, c_dir = 3 + 6 * n_deg_v, C = c_ipe + c_dir;
+    const int64_t total = (int64_t)n_rays * S * C;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = idx / C; int c = (int)(idx - row * C);
+        int ray = (int)(row / S), k = (int)(row - (int64_t)ray * S);
+        float v;
+        if (c < c_ipe) {
+            const float d[3] = {rays_d[3 * (size_t)ray], rays_d[3 * (size_t)ray + 1], rays_d[3 * (size_t)ray + 2]};
+            const float o[3] = {rays_o[3 * (size_t)ray], rays_o[3 * (size_t)ray + 1], rays_o[3 * (size_t)ray + 2]};
+            float dmag = fmaxf(1e-10f, d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            float mean[3], cov[3];
+            frustum_gaussian(z_vals[(size_t)ray * (S + 1) + k], z_vals[(size_t)ray * (S + 1) + k + 1], radii[ray], d, o, dmag, mean, cov);
+            int q = c < c_ipe / 2 ? c : c - c_ipe / 2;   // [y | y + pi/2]
+            int deg = q / 3 + min_deg, ax = q % 3;
+            float sc = exp2f((float)deg);
+            float y = mean[ax] * sc, yv = cov[ax] * sc * sc;
+            if (c >= c_ipe / 2) y += 1.5707963267948966f;
+            v = expf(-0.5f * yv) * sinf(y);
+            if (means_out && c < 3) { means_out[row * 3 + c] = mean[c]; covs_out[row * 3 + c] = cov[c]; }
+        } else {
+            int cc = c - c_ipe;
+            const float *vd = viewdirs + 3 * (size_t)ray;
+            if (cc < 3) v = vd[cc];
+            else { int q = cc - 3; int halfn = 3 * n_deg_v; int qq = q < halfn ? q : q - halfn; float x = vd[qq % 3] * exp2f((float)(qq / 3 + min_deg_view)); if (q >= halfn) x += 1.5707963267948966f; v = sinf(x); }
+        }
+        embedded[idx] = v;
+    }
+}
+
+// Mip-NeRF resample_along_rays + sorted_piecewise_constant_pdf (networks/utils/mip.py:146-176, :7-63), randomized=False or
+// caller-supplied jitter: one warp per ray, O(S log S) interval search instead of the reference's [N,S+2,S+1] mask.
+constexpr int MIP_MAX_S = 256;
+__global__ void __launch_bounds__(PDF_WARPS * 32) mip_resample_kernel(int n_rays, int S, float resample_padding, const float *__restrict__ z_vals, const float *__restrict__ weights,
+                                                                      const float *__restrict__ u_in, float *__restrict__ z_out) {
+    __shared__ float s_w[PDF_WARPS][MIP_MAX_S + 2];
+    __shared__ float s_cdf[PDF_WARPS][MIP_MAX_S + 2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ray = blockIdx.x * PDF_WARPS + wid;
+    if (ray >= n_rays) return;
+    const float *z = z_vals + (size_t)ray * (S + 1), *w_in = weights + (size_t)ray * S;
+    float *w = s_w[wid], *cdf = s_cdf[wid];
+    // blur: pad, pairwise max, pairwise mean, + padding constant (mip.py:154-163)
+    float part = 0.f;
+    for (int k = lane; k < S; k += 32) {
+        float wm1 = w_in[max(k - 1, 0)], w0 = w_in[k], wp1 = w_in[min(k + 1, S - 1)];
+        float v = 0.5f * (fmaxf(wm1, w0) + fmaxf(w0, wp1)) + resample_padding;
+        w[k] = v; part += v;
+    }
+    float wsum_all = wsum(part);
+    const float eps = 1e-5f;
+    float padding = fmaxf(0.f, eps - wsum_all);
+    const float add = padding / (float)S;
+    wsum_all += padding;
+    __syncwarp();
+    if (lane == 0) {
+        float c = 0.f; cdf[0] = 0.f;
+        for (int k = 0; k < S - 1; ++k) { c += (w[k] + add) / wsum_all; cdf[k + 1] = fminf(1.f, c); }
+        cdf[S] = 1.f;
+    }
+    __syncwarp();
+    const int num = S + 1;   // samples drawn == len(z_vals)
+    for (int j = lane; j < num; j += 32) {
+        float u;
+        if (u_in) u = u_in[(size_t)ray * num + j];
+        else { const float end = 1.f - 1.1920929e-07f; float step = end / (float)(num - 1); u = j < num / 2 ? step * (float)j : end - step * (float)(num - 1 - j); }
+        int lo = 0, hi = num;   // first index with cdf[idx] > u  (cdf has S+1 entries; cdf[0]=0 <= u always)
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+        int i0 = lo - 1, i1 = lo < num ? lo : num - 1;
+        float c0 = cdf[i0], c1 = cdf[i1], b0 = z[i0], b1 = z[i1];
+        float t = (u - c0) / (c1 - c0);
+        if (isnan(t)) t = 0.f;
+        t = fminf(fmaxf(t, 0.f), 1.f);
+        z_out[(size_t)ray * num + j] = b0 + t * (b1 - b0);
+    }
+}
+
 }  // namespace xrb
 
 using namespace xrb;
@@ -254,6 +351,27 @@ int xrb_nerf_posenc(const float *pts, const float *viewdirs, int64_t n_pts, int 
     int64_t blocks = (total + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
     posenc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n_pts, samples_per_ray, multires, multires_dirs, pts, viewdirs, embedded);
     return check_launch("posenc");
+}
+
+int xrb_mip_embed(const float *z_vals, const float *rays_o, const float *rays_d, const float *radii, const float *viewdirs, int n_rays, int n_samples, int min_deg_point,
+                  int max_deg_point, int min_deg_view, int max_deg_view, float *embedded, float *means_out, float *covs_out, void *stream) {
+    XRB_REQUIRE(n_rays >= 0 && n_samples >= 1 && max_deg_point > min_deg_point && max_deg_view >= min_deg_view, "mip_embed: bad size");
+    if (n_rays == 0) return XRB_OK;
+    XRB_REQUIRE(z_vals && rays_o && rays_d && radii && viewdirs && embedded && ((means_out == nullptr) == (covs_out == nullptr)), "mip_embed: null pointer");
+    int64_t total = (int64_t)n_rays * n_samples * (6 * (max_deg_point - min_deg_point) + 3 + 6 * (max_deg_view - min_deg_view));
+    int64_t blocks = (total + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
+    mip_embed_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n_rays, n_samples, min_deg_point, max_deg_point, min_deg_view, max_deg_view, z_vals, rays_o, rays_d, radii, viewdirs, embedded,
+                                                                   means_out, covs_out);
+    return check_launch("mip_embed");
+}
+
+int xrb_mip_resample(const float *z_vals, const float *weights, const float *u, int n_rays, int n_samples, float resample_padding, float *z_out, void *stream) {
+    XRB_REQUIRE(n_rays >= 0 && n_samples >= 2, "mip_resample: bad size");
+    if (n_samples > MIP_MAX_S) { set_error("mip_resample: n_samples <= 256 supported"); return XRB_E_UNSUPPORTED; }
+    if (n_rays == 0) return XRB_OK;
+    XRB_REQUIRE(z_vals && weights && z_out, "mip_resample: null pointer");
+    mip_resample_kernel<<<(n_rays + PDF_WARPS - 1) / PDF_WARPS, PDF_WARPS * 32, 0, (cudaStream_t)stream>>>(n_rays, n_samples, resample_padding, z_vals, weights, u, z_out);
+    return check_launch("mip_resample");
 }
 
 }  // extern "C"

@@ -53,12 +53,27 @@ int launch_field(const xrb_ngp_config *cfg, const void *table, const void *dens,
 __device__ __forceinline__ float round_h(float x) { return __half2float(__float2half_rn(x)); }
 
 __device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t z, uint32_t hashmap_size, uint32_t res) {
-    // tcnn grid.h grid_index(): dense strides while they fit, else the coherent prime hash
-    uint32_t stride = 1, index = 0;
-    index += x * stride; stride *= res;
-    if (stride <= hashmap_size) { index += y * stride; stride *= res; if (stride <= hashmap_size) { index += z * stride; stride *= res; } }
-    if (hashmap_size < stride) index = x ^ (y * 2654435761u) ^ (z * 805459861u);
-    return index % hashmap_size;
+    // tcnn grid.h grid_index(): dense strides while they fit, else the coherent prime hash; then `% hashmap_size`.
+    // The modulo is strength-reduced without changing its value (an integer division costs 3 XU-pipe ops on sm_100):
+    //   hashed levels have hashmap_size == 2^log2_hashmap_size (the cap)          -> mask;
+    //   dense levels have index <= res^3 + res^2 + res < 2 * hashmap_size          -> one conditional subtract.
+    if ((uint64_t)res * res * res > hashmap_size) {   // uniform per level
+        uint32_t h = x ^ (y * 2654435761u) ^ (z * 805459861u);
+        return (hashmap_size & (hashmap_size - 1)) == 0 ? (h & (hashmap_size - 1)) : (h % hashmap_size);
+    }
+    uint32_t index = x + y * res + z * res * res;
+    return index >= hashmap_size ? index - hashmap_size : index;
+}
+
+// floor() of 0 <= p < 2^22 and its integer value on the FMA/ALU pipes (F2I / FRND / I2F are quarter-rate XU ops):
+// t = p + 1.5*2^23 rounds p to the nearest integer into the low mantissa bits; one compare fixes round-up to floor. Exact.
+__device__ __forceinline__ float floor_small(float p, uint32_t *ip) {
+    float t = __fadd_rn(p, 12582912.0f);
+    float r = __fadd_rn(t, -12582912.0f);
+    int i = __float_as_int(t) - 0x4B400000;
+    if (r > p) { r = __fadd_rn(r, -1.0f); i -= 1; }
+    *ip = (uint32_t)i;
+    return r;
 }
 
 // one level of the multiresolution hash encoding: returns the two interpolated features (fp32, NOT yet rounded)
@@ -67,8 +82,8 @@ __device__ __forceinline__ float2 hash_level(const __half2 *__restrict__ table, 
     const __half2 *tl = table + g.offset[l];
     const float sc = g.scale[l];
     float px = __fmaf_rn(sc, x, 0.5f), py = __fmaf_rn(sc, y, 0.5f), pz = __fmaf_rn(sc, z, 0.5f);
-    float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-    uint32_t gx = (uint32_t)(int)fx, gy = (uint32_t)(int)fy, gz = (uint32_t)(int)fz;
+    uint32_t gx, gy, gz;
+    float fx = floor_small(px, &gx), fy = floor_small(py, &gy), fz = floor_small(pz, &gz);
     fx = px - fx; fy = py - fy; fz = pz - fz;
     __half2 v[8];
 #pragma unroll

@@ -3,6 +3,8 @@
 // shared memory), impl 1 = tcgen05 tensor-core tiles (tc_field.cuh). Both follow the numeric contract in
 // oracle/tcnn_oracle.c (fp16 operands, fp32 accumulate, fp16 activations).
 #include "tc_field.cuh"
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace xrb {
 
@@ -173,10 +175,12 @@ __global__ void __launch_bounds__(128 * TC_WG, 2) ngp_field_tc_kernel(HashGridDe
     tc_cta_teardown<TC_TMEM_COLS>(tmem_base);
 }
 
-static int persistent_grid(const void *kernel, int block, size_t smem, int work_ctas) {
+static int persistent_grid(const void *kernel, int block, size_t smem, int work_ctas, int min_per_sm = 1) {
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
-    if (per_sm < 1) per_sm = 1;
+    cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem);
+    if (getenv("XRB_DEBUG")) fprintf(stderr, "[xrb] occupancy query: err=%d per_sm=%d block=%d smem=%zu\n", (int)oe, per_sm, block, smem);
+    if (oe != cudaSuccess) cudaGetLastError();
+    if (per_sm < min_per_sm) per_sm = min_per_sm;  // the calculator has been seen to under-report; extra CTAs simply queue
     int dev = 0, sms = NUM_SMS; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int g = sms * per_sm;
     return work_ctas < g ? (work_ctas > 0 ? work_ctas : 1) : g;
@@ -272,7 +276,7 @@ int launch_field(const xrb_ngp_config *cfg, const void *table, const void *dens,
         const void *k = density_only ? (const void *)ngp_field_tc_kernel<true> : (const void *)ngp_field_tc_kernel<false>;
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int n_tiles = (n + 127) / 128;
-        int grid = persistent_grid(k, 128 * TC_WG, smem, (n_tiles + TC_WG - 1) / TC_WG);
+        int grid = persistent_grid(k, 128 * TC_WG, smem, (n_tiles + TC_WG - 1) / TC_WG, 2);
         if (density_only)
             ngp_field_tc_kernel<true><<<grid, 128 * TC_WG, smem, s>>>(g, (const __half2 *)table, image, image_bytes, cfg->density_hidden, cfg->color_hidden, pts, pts_stride, dirs, dirs_stride, n, n_dev, out);
         else

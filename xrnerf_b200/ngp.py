@@ -66,6 +66,23 @@ class NgpField(nn.Module):
                                             pts.stride(0), _C.ptr(dirs), dirs.stride(0), n, _C.ptr(raw), impl, _C.stream()), 'ngp_mlp_forward')
         return raw
 
+    def forward(self, pts, dirs):
+        """differentiable (w.r.t. the parameters) HashNerfMLP.run_mlp"""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in (self.hash_params, self.density_params, self.color_params)):
+            return _FieldFn.apply(self, pts, dirs, self.hash_params, self.density_params, self.color_params)
+        return self.run_mlp(pts, dirs)
+
+    def backward_params(self, pts, dirs, grad_raw, out=None):
+        """dL/draw [S,4] -> (d_hash, d_density, d_color) fp32, accumulated into `out` if given (zero-initialised otherwise)."""
+        _C.require_cuda(pts, dirs, grad_raw)
+        self.refresh()
+        if out is None:
+            out = (torch.zeros_like(self.hash_params), torch.zeros_like(self.density_params), torch.zeros_like(self.color_params))
+        n = pts.shape[0]
+        _C.check(_C.lib.xrb_ngp_mlp_backward(self.cfg, _C.ptr(self._table16), _C.ptr(self._dens16), _C.ptr(self._color16), _C.ptr(pts), pts.stride(0), _C.ptr(dirs),
+                                             dirs.stride(0), _C.ptr(grad_raw), n, _C.ptr(out[0]), _C.ptr(out[1]), _C.ptr(out[2]), _C.stream()), 'ngp_mlp_backward')
+        return out
+
     def run_density(self, pts, impl=None):
         _C.require_cuda(pts)
         self.refresh()
@@ -76,6 +93,26 @@ class NgpField(nn.Module):
         _C.check(_C.lib.xrb_ngp_density_forward(self.cfg, _C.ptr(self._table16), _C.ptr(self._dens16), _C.ptr(self._image), _C.ptr(pts), pts.stride(0), n,
                                                 _C.ptr(out), impl, _C.stream()), 'ngp_density_forward')
         return out
+
+
+class _FieldFn(torch.autograd.Function):
+    """autograd bridge for NgpField.run_mlp: forward = xrb_ngp_mlp_forward, backward = xrb_ngp_mlp_backward (one kernel
+    producing the gradients of all three parameter vectors). pts/dirs are not differentiated (the reference detaches them,
+    hashnerf_mlp.py:58-68)."""
+
+    @staticmethod
+    def forward(ctx, field, pts, dirs, hash_params, density_params, color_params):
+        ctx.field = field
+        ctx.save_for_backward(pts, dirs)
+        return field.run_mlp(pts, dirs)
+
+    @staticmethod
+    def backward(ctx, grad_raw):
+        f = ctx.field
+        pts, dirs = ctx.saved_tensors
+        grad_raw = grad_raw.contiguous().to(torch.float32)
+        dt, dd, dc = f.backward_params(pts, dirs, grad_raw)
+        return None, None, None, dt, dd, dc
 
 
 class NgpRenderer:
