@@ -1,0 +1,126 @@
+"""NerfMLP / HashNerfMLP with the reference's kwargs, state_dict keys and data-dict protocol
+(/root/reference/xrnerf/models/mlps/nerf_mlp.py:11-94, hashnerf_mlp.py:23-111)."""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import builder
+from .builder import MLPS
+from ..ngp import NgpField, PER_LEVEL_SCALE
+
+
+@MLPS.register_module()
+class BaseMLP(nn.Module):
+    def __init__(self, **kwarg):
+        super().__init__()
+
+
+@MLPS.register_module()
+class NerfMLP(BaseMLP):
+    """8x256 ReLU MLP with skip at layer 4 and a 128-wide view branch; parameters are nn.Linear modules with the reference's
+    names (pts_linears.i, views_linears.0, feature_linear, alpha_linear, rgb_linear) so reference checkpoints load.
+
+    The dense layers are plain library GEMMs here (cuBLAS through torch, TF32 off = fp32 like the reference's default on
+    torch>=1.12); the embedding before them and the compositing after them are this package's kernels. The tcgen05
+    fused 256-wide chain is the planned replacement."""
+
+    def __init__(self, skips=[4], netdepth=8, netwidth=256, output_ch=4, use_viewdirs=True, netchunk=1024 * 32, embedder=None, **kwarg):
+        super().__init__()
+        self.skips, self.chunk, self.use_viewdirs = skips, netchunk, use_viewdirs
+        self.embedder = builder.build_embedder(embedder)
+        D, W = netdepth, netwidth
+        self.input_ch, self.input_ch_dirs = self.embedder.get_embed_ch()
+        self.pts_linears = nn.ModuleList([nn.Linear(self.input_ch, W)] + [nn.Linear(W, W) if i not in self.skips else nn.Linear(W + self.input_ch, W) for i in range(D - 1)])
+        if self.use_viewdirs:
+            self.views_linears = nn.ModuleList([nn.Linear(self.input_ch_dirs + W, W // 2)])
+            self.feature_linear = nn.Linear(W, W)
+            self.alpha_linear = nn.Linear(W, 1)
+            self.rgb_linear = nn.Linear(W // 2, 3)
+        else:
+            self.output_linear = nn.Linear(W, output_ch)
+
+    def forward(self, data):
+        data = self.embedder(data)
+        out = self.batchify_run_mlp(data['embedded'])
+        data['raw'] = torch.reshape(out, list(data['unflatten_shape']) + [out.shape[-1]])
+        del data['unflatten_shape']
+        return data
+
+    def batchify_run_mlp(self, x):
+        if self.chunk is None:
+            return self.run_mlp(x)
+        return torch.cat([self.run_mlp(x[i:i + self.chunk]) for i in range(0, x.shape[0], self.chunk)], 0)
+
+    def run_mlp(self, x):
+        input_pts, input_views = torch.split(x, [self.input_ch, self.input_ch_dirs], dim=-1)
+        h = input_pts
+        for i, l in enumerate(self.pts_linears):
+            h = F.relu(l(h))
+            if i in self.skips:
+                h = torch.cat([input_pts, h], -1)
+        if self.use_viewdirs:
+            alpha = self.alpha_linear(h)
+            h = torch.cat([self.feature_linear(h), input_views], -1)
+            for l in self.views_linears:
+                h = F.relu(l(h))
+            return torch.cat([self.rgb_linear(h), alpha], -1)
+        return self.output_linear(h)
+
+
+class _ParamHolder(nn.Module):
+    """gives a flat parameter the reference's state_dict key `<name>.params` (tcnn modules expose exactly one `params`)"""
+
+    def __init__(self, p):
+        super().__init__()
+        self.params = p
+
+
+def _hidden(network_config):
+    if 'n_hidden_layers' in network_config:
+        return int(network_config['n_hidden_layers'])
+    return int(network_config.get('num_layers', 5))  # the reference's key is num_layers; tcnn's default would be 5
+
+
+@MLPS.register_module()
+class HashNerfMLP(BaseMLP):
+    """state_dict keys: embedder_pos.params, embedder_dir.params (empty), density_net.params, color_net.params."""
+
+    def __init__(self, bound=1, embedder_pos=None, embedder_dir=None, density_net=None, color_net=None, impl=1, **kwarg):
+        super().__init__()
+        enc = dict(embedder_pos['encoding_config'])
+        if enc.get('otype') != 'HashGrid' or embedder_dir['encoding_config'].get('otype') != 'SphericalHarmonics' or int(embedder_dir['encoding_config'].get('degree', 4)) != 4:
+            raise NotImplementedError('HashNerfMLP: HashGrid position encoding + SphericalHarmonics degree 4 (the reference config)')
+        if int(density_net['n_output_dims']) != 16 or int(color_net['n_output_dims']) != 3:
+            raise NotImplementedError('HashNerfMLP: density_net 16 outputs, color_net 3 outputs (the reference config)')
+        field = NgpField(n_levels=int(enc.get('n_levels', 16)), n_features=int(enc.get('n_features_per_level', 2)), log2_hashmap_size=int(enc.get('log2_hashmap_size', 19)),
+                              base_resolution=int(enc.get('base_resolution', 16)), per_level_scale=PER_LEVEL_SCALE,  # get_per_level_scale(1): ignores `bound` (Q6)
+                              width=int(density_net['network_config'].get('n_neurons', 64)), density_hidden=_hidden(density_net['network_config']),
+                              color_hidden=_hidden(color_net['network_config']), impl=impl)
+        # not registered as a sub-module: its Parameters are the very objects held by the four tcnn-named holders below, so
+        # state_dict()/load_state_dict() see exactly the reference's keys and .to()/.cuda() (in-place on .data) still moves them
+        self.__dict__['field'] = field
+        f = field
+        self.embedder_pos = _ParamHolder(f.hash_params)
+        self.embedder_dir = _ParamHolder(nn.Parameter(torch.zeros(0)))
+        self.density_net = _ParamHolder(f.density_params)
+        self.color_net = _ParamHolder(f.color_params)
+
+    def forward(self, data):
+        shape = data['pts'].shape[:-1]
+        out = self.run_mlp(data)
+        data['raw'] = torch.reshape(out, list(shape) + [out.shape[-1]])
+        return data
+
+    def run_mlp(self, data):
+        pts, viewdirs = data['pts'], data['viewdirs']
+        if pts.dim() > viewdirs.dim():
+            viewdirs = viewdirs[:, None].expand(pts.shape)
+        pts, viewdirs = pts.reshape(-1, 3).detach(), viewdirs.reshape(-1, 3).detach()
+        if pts.stride(-1) != 1:
+            pts = pts.contiguous()
+        if viewdirs.stride(-1) != 1:
+            viewdirs = viewdirs.contiguous()
+        return self.field(pts.float(), viewdirs.float())
+
+    def run_density(self, pts_flat):
+        return self.field.run_density(pts_flat.float() if pts_flat.stride(-1) == 1 else pts_flat.contiguous().float())
