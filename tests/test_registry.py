@@ -72,7 +72,8 @@ def test_nerf_network_forward_and_train_step_vs_numpy_oracle():
     z = np.broadcast_to(np.linspace(2, 6, s, dtype=np.float32), (n, s)).copy()
     pts = o[:, None] + d[:, None] * z[..., None]
     data = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in dict(rays_o=o, rays_d=d, viewdirs=vd, z_vals=z, pts=pts, target_s=rng.random((n, 3)).astype(np.float32)).items()}
-    ret = net.forward(dict(data), is_test=True)
+    with torch.no_grad():
+        ret = net.forward(dict(data), is_test=True)
     # oracle chain with the same weights
     sd = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
     raw = O.nerf_mlp(sd, O.embed(pts, vd), 63, 27, prefix='mlp.').reshape(n, s, 4)

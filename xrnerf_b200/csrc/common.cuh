@@ -91,7 +91,11 @@ __device__ __forceinline__ float calc_dt(float t, float cone) { return clampf(mu
 
 // frexpf exponent for finite positive normal/zero inputs (the only ones the march produces); matches frexpf incl. 0 -> 0
 __device__ __forceinline__ int frexp_exponent(float v) {
-    int e; frexpf(v, &e); return e;
+    // v >= 0 finite. Normal numbers: biased exponent - 126 (frexpf's convention 0.5 <= m < 1); zero -> 0; denormals take libm.
+    uint32_t e = __float_as_uint(v) >> 23;
+    if (e != 0) return (int)e - 126;
+    if (v == 0.f) return 0;
+    int r; frexpf(v, &r); return r;
 }
 __device__ __forceinline__ int mip_from_pos(float px, float py, float pz) {  // ray_sampler_header.h:37-43
     float m = fmaxf(fabsf(sub_(px, 0.5f)), fmaxf(fabsf(sub_(py, 0.5f)), fabsf(sub_(pz, 0.5f))));
@@ -129,7 +133,7 @@ __device__ __forceinline__ float distance_to_next_voxel(const float p[3], const 
         t3[k] = mul_(sub_(floorf(add_(add_(pr, 0.5f), mul_(0.5f, signf_(d[k])))), pr), idir[k]);
     }
     float t = fminf(fminf(t3[0], t3[1]), t3[2]);
-    return fmaxf(div_(t, (float)res), 0.0f);
+    return fmaxf(mul_(t, __uint_as_float((254u - (__float_as_uint((float)res) >> 23)) << 23)), 0.0f);  // t / res, res = 2^k: exact reciprocal, same bits as the division
 }
 __device__ __forceinline__ float advance_to_next_voxel(float t, float cone, const float p[3], const float d[3], const float idir[3], uint32_t res) {  // :282-296
     float t_target = add_(t, distance_to_next_voxel(p, d, idir, res));

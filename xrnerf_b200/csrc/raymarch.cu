@@ -24,9 +24,11 @@ int check_launch(const char *what) {
 
 // ============================================================================ ray march
 // One thread per ray. emit==false: count steps (ray_sampler.cu:58-72). emit==true: write rows (:99-115).
+constexpr uint32_t TCAP = 64;  // per-ray sample-t slots cached by the count pass; rays with more samples are re-marched by the emit pass
+
 template <bool EMIT>
 __device__ __forceinline__ uint32_t march_ray(const float o[3], const float d[3], float lo, float hi, float startt, float cone,
-                                              const uint8_t *__restrict__ bitfield, uint32_t limit, float *__restrict__ coords) {
+                                              const uint8_t *__restrict__ bitfield, uint32_t limit, float *__restrict__ coords, float *__restrict__ tbuf = nullptr) {
     const float idir[3] = {div_(1.0f, d[0]), div_(1.0f, d[1]), div_(1.0f, d[2])};
     float wdir[3], diag = sub_(hi, lo);
     if (EMIT) { wdir[0] = mul_(add_(d[0], 1.0f), 0.5f); wdir[1] = mul_(add_(d[1], 1.0f), 0.5f); wdir[2] = mul_(add_(d[2], 1.0f), 0.5f); }
@@ -42,7 +44,7 @@ __device__ __forceinline__ uint32_t march_ray(const float o[3], const float d[3]
                 c[0] = div_(sub_(p[0], lo), diag); c[1] = div_(sub_(p[1], lo), diag); c[2] = div_(sub_(p[2], lo), diag);  // warp_position
                 c[3] = warp_dt(dt);
                 c[4] = wdir[0]; c[5] = wdir[1]; c[6] = wdir[2];
-            }
+            } else if (tbuf && j < TCAP) tbuf[j] = t;
             ++j; t = add_(t, dt);
         } else {
             t = advance_to_next_voxel(t, cone, p, d, idir, NERF_GRIDSIZE >> mip);
@@ -58,14 +60,15 @@ struct MarchWs {  // device workspace layout for N rays
     float *startt;         // [N]
     uint32_t *block_sum;   // [n_blocks] -> exclusive block offsets after scan
     uint32_t *misc;        // [4]: base0, ray0, total
+    float *tbuf;           // [N][TCAP] sample t values found by the count pass
 };
 __host__ __device__ inline size_t march_ws_bytes(int n) {
     size_t nb = (size_t)(n + MARCH_BLOCK - 1) / MARCH_BLOCK;
-    return sizeof(uint32_t) * ((size_t)n * 2 + nb + 16);
+    return sizeof(uint32_t) * ((size_t)n * 2 + nb + 16 + (size_t)n * TCAP);
 }
 inline MarchWs march_ws(void *ws, int n) {
     size_t nb = (size_t)(n + MARCH_BLOCK - 1) / MARCH_BLOCK;
-    MarchWs w; w.local_excl = (uint32_t *)ws; w.startt = (float *)(w.local_excl + n); w.block_sum = (uint32_t *)(w.startt + n); w.misc = w.block_sum + nb;
+    MarchWs w; w.local_excl = (uint32_t *)ws; w.startt = (float *)(w.local_excl + n); w.block_sum = (uint32_t *)(w.startt + n); w.misc = w.block_sum + nb; w.tbuf = (float *)(w.misc + 16);
     return w;
 }
 
@@ -86,7 +89,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total)
 __global__ void __launch_bounds__(MARCH_BLOCK) march_count_kernel(int n_rays, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
                                                                   const uint8_t *__restrict__ bitfield, float lo, float hi, float near_distance, float cone,
                                                                   Pcg32 rng, uint32_t *__restrict__ local_excl, float *__restrict__ startt_out,
-                                                                  uint32_t *__restrict__ block_sum, int32_t *__restrict__ numsteps) {
+                                                                  uint32_t *__restrict__ block_sum, int32_t *__restrict__ numsteps, float *__restrict__ tbuf) {
     uint32_t i = blockIdx.x * MARCH_BLOCK + threadIdx.x;
     uint32_t n = 0;
     if (i < (uint32_t)n_rays) {
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(MARCH_BLOCK) march_count_kernel(int n_rays, co
         float d[3] = {rays_d[3 * (size_t)i], rays_d[3 * (size_t)i + 1], rays_d[3 * (size_t)i + 2]};
         float st = ray_start_t(rng, i, lo, hi, o, d, near_distance, cone);
         startt_out[i] = st;
-        n = march_ray<false>(o, d, lo, hi, st, cone, bitfield, NERF_STEPS, nullptr);
+        n = march_ray<false>(o, d, lo, hi, st, cone, bitfield, NERF_STEPS, nullptr, tbuf ? tbuf + (size_t)i * TCAP : nullptr);
         numsteps[2 * (size_t)i] = (int32_t)n;
     }
     uint32_t tot;
@@ -131,28 +134,46 @@ __global__ void __launch_bounds__(1024) march_scan_kernel(int n_blocks, uint32_t
     }
 }
 
-__global__ void __launch_bounds__(MARCH_BLOCK) march_emit_kernel(int n_rays, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
-                                                                 const uint8_t *__restrict__ bitfield, float lo, float hi, float cone, uint32_t max_samples,
-                                                                 const uint32_t *__restrict__ local_excl, const float *__restrict__ startt,
-                                                                 const uint32_t *__restrict__ block_off, const uint32_t *__restrict__ misc,
-                                                                 float *__restrict__ coords_out, int32_t *__restrict__ rays_index, int32_t *__restrict__ numsteps,
-                                                                 int32_t *__restrict__ counters) {
-    uint32_t i = blockIdx.x * MARCH_BLOCK + threadIdx.x;
+// Emit pass, one WARP per ray: lanes rebuild rows from the cached t values (pos = o + t d and dt = calc_dt(t) are the very
+// expressions of the march, so the rows are bit-identical to a second march) and write 32 consecutive 28-byte rows per step.
+// Rays longer than TCAP are re-marched by lane 0 (ray_sampler.cu:99-115).
+__global__ void __launch_bounds__(256) march_emit_kernel(int n_rays, const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ bitfield, float lo,
+                                                         float hi, float cone, uint32_t max_samples, const uint32_t *__restrict__ local_excl, const float *__restrict__ startt,
+                                                         const uint32_t *__restrict__ block_off, const uint32_t *__restrict__ misc, const float *__restrict__ tbuf,
+                                                         float *__restrict__ coords_out, int32_t *__restrict__ rays_index, int32_t *__restrict__ numsteps,
+                                                         int32_t *__restrict__ counters) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = (blockIdx.x * 256 + threadIdx.x) >> 5;
     bool ok = false;
     if (i < (uint32_t)n_rays) {
         uint32_t n = (uint32_t)numsteps[2 * (size_t)i];
-        uint32_t base = misc[0] + block_off[blockIdx.x] + local_excl[i];
+        uint32_t base = misc[0] + block_off[i / MARCH_BLOCK] + local_excl[i];
+        __syncwarp();
         if (base + n > max_samples) {  // ray_sampler.cu:76-82
-            numsteps[2 * (size_t)i] = 0; numsteps[2 * (size_t)i + 1] = (int32_t)base;
+            if (lane == 0) { numsteps[2 * (size_t)i] = 0; numsteps[2 * (size_t)i + 1] = (int32_t)base; }
         } else {
-            ok = true;
-            numsteps[2 * (size_t)i + 1] = (int32_t)base;
-            // serial-order equivalent of `ray_idx = atomicAdd(ray_counter,1)`: slots are a prefix of the rays
-            rays_index[i] = n == 0 ? -1 : (int32_t)(misc[1] + i);
+            ok = lane == 0;
+            if (lane == 0) {
+                numsteps[2 * (size_t)i + 1] = (int32_t)base;
+                // serial-order equivalent of `ray_idx = atomicAdd(ray_counter,1)`: slots are a prefix of the rays
+                rays_index[i] = n == 0 ? -1 : (int32_t)(misc[1] + i);
+            }
             if (n > 0) {
-                float o[3] = {rays_o[3 * (size_t)i], rays_o[3 * (size_t)i + 1], rays_o[3 * (size_t)i + 2]};
-                float d[3] = {rays_d[3 * (size_t)i], rays_d[3 * (size_t)i + 1], rays_d[3 * (size_t)i + 2]};
-                march_ray<true>(o, d, lo, hi, startt[i], cone, bitfield, n, coords_out + 7 * (size_t)base);
+                const float o[3] = {rays_o[3 * (size_t)i], rays_o[3 * (size_t)i + 1], rays_o[3 * (size_t)i + 2]};
+                const float d[3] = {rays_d[3 * (size_t)i], rays_d[3 * (size_t)i + 1], rays_d[3 * (size_t)i + 2]};
+                if (n <= TCAP) {
+                    const float diag = sub_(hi, lo);
+                    const float w0 = mul_(add_(d[0], 1.0f), 0.5f), w1 = mul_(add_(d[1], 1.0f), 0.5f), w2 = mul_(add_(d[2], 1.0f), 0.5f);
+                    for (uint32_t j = lane; j < n; j += 32) {
+                        float t = tbuf[(size_t)i * TCAP + j];
+                        float *c = coords_out + 7 * (size_t)(base + j);
+                        c[0] = div_(sub_(add_(o[0], mul_(t, d[0])), lo), diag); c[1] = div_(sub_(add_(o[1], mul_(t, d[1])), lo), diag); c[2] = div_(sub_(add_(o[2], mul_(t, d[2])), lo), diag);
+                        c[3] = warp_dt(calc_dt(t, cone));
+                        c[4] = w0; c[5] = w1; c[6] = w2;
+                    }
+                } else if (lane == 0) {
+                    march_ray<true>(o, d, lo, hi, startt[i], cone, bitfield, n, coords_out + 7 * (size_t)base);
+                }
             }
         }
     }
@@ -451,10 +472,10 @@ int xrb_rm_rays_sampler(const float *rays_o, const float *rays_d, const uint8_t 
     MarchWs w = march_ws(workspace, n_rays);
     int nb = (n_rays + MARCH_BLOCK - 1) / MARCH_BLOCK;
     Pcg32 rng = host_rng(seed, n_prior_calls);
-    march_count_kernel<<<nb, MARCH_BLOCK, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, near_distance, cone_angle, rng, w.local_excl, w.startt, w.block_sum, numsteps);
+    march_count_kernel<<<nb, MARCH_BLOCK, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, near_distance, cone_angle, rng, w.local_excl, w.startt, w.block_sum, numsteps, w.tbuf);
     march_scan_kernel<<<1, 1024, 0, s>>>(nb, w.block_sum, w.misc, counters);
-    march_emit_kernel<<<nb, MARCH_BLOCK, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, cone_angle, (uint32_t)max_samples, w.local_excl, w.startt, w.block_sum,
-                                                 w.misc, coords_out, rays_index, numsteps, counters);
+    march_emit_kernel<<<(int)(((size_t)n_rays * 32 + 255) / 256), 256, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, cone_angle, (uint32_t)max_samples, w.local_excl, w.startt,
+                                                                             w.block_sum, w.misc, w.tbuf, coords_out, rays_index, numsteps, counters);
     return check_launch("rays_sampler");
 }
 
