@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 N_RAYS = 65536
 BUDGET = 64          # max samples per ray the workspace is sized for (reference: 1024; measured mean is ~11-30)
-N_BATCHES = 8        # distinct ray batches cycled through
+N_BATCHES = 96       # distinct ray batches cycled through: 96 x 1.5 MiB of rays = 151 MB > 126 MB L2 (inputs larger than L2)
 METRIC = 'rays/sec (inference render, Instant-NGP lego-shaped 800x800, 65536 rays/batch)'
 WORKLOAD = 'instant-ngp lego-like synthetic (configs[1]): 65536 rays/batch from 40 spiral 800x800 views, occupancy-grid march + hash(16x2,T=2^19) + SH4 + MLP(64;1+2 hidden) + composite, forward'
 BYTES_PER_SAMPLE = 512 + 28 + 16
@@ -82,11 +82,11 @@ class ClockSampler:
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons, 'samples': len(sm)}
 
 
-def make_scene(rank):
+def make_scene(rank, n_batches=N_BATCHES):
     from xrnerf_b200 import synth
     grid = synth.lego_like_density_grid(0)
     bf, _ = synth.bitfield_from_grid_numpy(grid)
-    batches = [synth.ray_batch(N_RAYS, seed=1000 * rank + b)[:2] for b in range(N_BATCHES)]
+    batches = [synth.ray_batch(N_RAYS, seed=1000 * rank + b)[:2] for b in range(n_batches)]
     table, dens, color = synth.ngp_weights(seed=0)
     return bf, batches, (table, dens, color)
 
@@ -100,7 +100,7 @@ def cpu_reference_rate(sample_rays, reps=1):
     port = O.Port()
     use_ref = O.have_ref()
     ref = O.Ref(serial=False) if use_ref else None
-    bf, batches, (table, dens, color) = make_scene(0)
+    bf, batches, (table, dens, color) = make_scene(0, 1)
     o, d = batches[0][0][:sample_rays], batches[0][1][:sample_rays]
     m = ref or port
     best = None
@@ -172,73 +172,101 @@ def run_ours(args):
     field = NgpField().to(dev)
     with torch.no_grad():
         field.hash_params.copy_(torch.from_numpy(table).to(dev)); field.density_params.copy_(torch.from_numpy(dens).to(dev)); field.color_params.copy_(torch.from_numpy(color).to(dev))
-    renderer = NgpRenderer(field, samples_per_ray_budget=BUDGET)
+    P = max(1, args.pipeline)   # batches in flight: step i runs on stream i % P with its own workspace, so the (latency-bound) march of
+    renderers = [NgpRenderer(field, samples_per_ray_budget=BUDGET) for _ in range(P)]   # batch i+1 overlaps the field kernel of batch i
+    streams = [torch.cuda.Stream(device=dev) for _ in range(P)]
     dev_batches = [(torch.from_numpy(o).to(dev), torch.from_numpy(d).to(dev)) for (o, d) in batches]
-    host_batches = [(torch.from_numpy(o).pin_memory(), torch.from_numpy(d).pin_memory()) for (o, d) in batches]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    host_batches = [(torch.from_numpy(o).pin_memory(), torch.from_numpy(d).pin_memory()) for (o, d) in batches[:8]]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    main = torch.cuda.current_stream()
+
+    def fork():
+        e = torch.cuda.Event(); e.record(main)
+        for st in streams:
+            st.wait_event(e)
+
+    def join():
+        for st in streams:
+            e = torch.cuda.Event(); e.record(st); main.wait_event(e)
+
     # ---- device-resident arm
     K, W = args.steps, args.warmup
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     evf = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    fork()
     for i in range(W):
-        renderer.render(*dev_batches[i % N_BATCHES], bf)
+        with torch.cuda.stream(streams[i % P]):
+            renderers[i % P].render(*dev_batches[i % N_BATCHES], bf)
+    join()
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    samples_total = 0
     counters_log = []
-    t_wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    fork()
     for i in range(K):
-        flush.fill_(i & 0xff)                        # L2 flush, outside the per-step events
-        for e in evf[i]:
-            e.record()                               # materialise the cudaEvent_t handles
-        _C.lib.xrb_ngp_render_set_profile_events(_C.C.c_void_p(evf[i][0].cuda_event), _C.C.c_void_p(evf[i][1].cuda_event))
-        ev[i][0].record()
-        out = renderer.render(*dev_batches[(W + i) % N_BATCHES], bf)
-        ev[i][1].record()
-        counters_log.append(out[3].clone())
+        st = streams[i % P]
+        with torch.cuda.stream(st):
+            for e in evf[i]:
+                e.record(st)                          # materialise the cudaEvent_t handles
+            _C.lib.xrb_ngp_render_set_profile_events(_C.C.c_void_p(evf[i][0].cuda_event), _C.C.c_void_p(evf[i][1].cuda_event))
+            out = renderers[i % P].render(*dev_batches[(W + i) % N_BATCHES], bf)
+            counters_log.append(out[3].clone())
     _C.lib.xrb_ngp_render_set_profile_events(None, None)
+    join()
+    e1.record(main)
     barrier()
-    t_wall = time.perf_counter() - t_wall0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
     field_ms = [a.elapsed_time(b) for a, b in evf]
     samples = [int(c[1].item()) for c in counters_log]
-    samples_total = sum(samples)
-    total_ms = float(sum(step_ms))
+    total_ms = float(e0.elapsed_time(e1))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     clk = clocks.stop() if rank == 0 else None
 
-    # ---- end-to-end arm: host (pinned) rays in, rgb+alpha out, every step
-    rgb_h = torch.empty((N_RAYS, 3), dtype=torch.float32).pin_memory()
-    alpha_h = torch.empty((N_RAYS, 1), dtype=torch.float32).pin_memory()
-    o_d = torch.empty((N_RAYS, 3), dtype=torch.float32, device=dev); d_d = torch.empty((N_RAYS, 3), dtype=torch.float32, device=dev)
+    # ---- end-to-end arm: host (pinned) rays in, rgb+alpha out, every step, through the public API; P batches in flight
+    slots = [dict(rgb_h=torch.empty((N_RAYS, 3), dtype=torch.float32).pin_memory(), alpha_h=torch.empty((N_RAYS, 1), dtype=torch.float32).pin_memory(),
+                  o_d=torch.empty((N_RAYS, 3), dtype=torch.float32, device=dev), d_d=torch.empty((N_RAYS, 3), dtype=torch.float32, device=dev), done=None) for _ in range(P)]
 
     def e2e_step(i):
-        o_h, d_h = host_batches[i % N_BATCHES]
-        o_d.copy_(o_h, non_blocking=True); d_d.copy_(d_h, non_blocking=True)
-        rgb, alpha, _, _ = renderer.render(o_d, d_d, bf)
-        rgb_h.copy_(rgb, non_blocking=True); alpha_h.copy_(alpha, non_blocking=True)
-        torch.cuda.current_stream().synchronize()   # the caller owns the pixels when the call returns
+        sl, st = slots[i % P], streams[i % P]
+        if sl['done'] is not None:
+            sl['done'].synchronize()                 # the caller consumes the pixels of the batch that used this slot before reusing it
+        o_h, d_h = host_batches[i % len(host_batches)]
+        with torch.cuda.stream(st):
+            sl['o_d'].copy_(o_h, non_blocking=True); sl['d_d'].copy_(d_h, non_blocking=True)
+            rgb, alpha, _, _ = renderers[i % P].render(sl['o_d'], sl['d_d'], bf)
+            sl['rgb_h'].copy_(rgb, non_blocking=True); sl['alpha_h'].copy_(alpha, non_blocking=True)
+            sl['done'] = torch.cuda.Event(); sl['done'].record(st)
+
+    def e2e_drain():
+        for sl in slots:
+            if sl['done'] is not None:
+                sl['done'].synchronize(); sl['done'] = None
+    fork()
     for i in range(W):
         e2e_step(i)
+    e2e_drain()
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record(main)
+    fork()
     for i in range(K):
         e2e_step(W + i)
-    e1.record()
+    e2e_drain()
+    join()
+    g1.record(main)
     barrier()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = torch.tensor([max(g0.elapsed_time(g1), 0.0)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
@@ -253,11 +281,11 @@ def run_ours(args):
             'metric': METRIC, 'value': world * N_RAYS * K / (total_ms_max * 1e-3), 'unit': 'rays/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': total_ms_max / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'rays_per_step_per_gpu': N_RAYS, 'samples_per_ray_mean': s_mean / N_RAYS, 'parallelism': f'ray-sharded x{world}, no data-path collective',
-                       'l2': 'flushed between steps (256 MiB fill, outside the per-step CUDA events)', 'timing': 'sum of per-step CUDA-event durations, max over ranks',
-                       'wall_ms_incl_flush': t_wall * 1e3},
+                       'l2': f'inputs larger than L2: {N_BATCHES} distinct ray batches = {N_BATCHES * N_RAYS * 24 / 1e6:.0f} MB cycled (L2 126 MB); the 24.4 MB fp16 hash table stays L2-resident as in production',
+                       'timing': 'one CUDA-event pair around the K steps on the launching stream, max over ranks', 'batches_in_flight': P},
             'clocks': clk,
             'e2e': {'value': world * N_RAYS * K / (e2e_ms * 1e-3), 'unit': 'rays/s', 'h2d_bytes_per_step': N_RAYS * 24, 'd2h_bytes_per_step': N_RAYS * 16,
-                    'ms_per_step': e2e_ms / K},
+                    'ms_per_step': e2e_ms / K, 'host_wall_ms_per_step': e2e_wall_ms / K},
             'gpu_launches': 5 * K,
             'roofline': {'kernel': 'xrb::ngp_field_tc_kernel<false>', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
                          'peak_source': peak_src, 'kernel_ms': f_ms, 'kernel_share_of_step': f_ms / (total_ms_max / K),
@@ -276,6 +304,7 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--pipeline', type=int, default=2, help='ray batches in flight (CUDA streams); 1 = strictly sequential steps')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':

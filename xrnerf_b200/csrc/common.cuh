@@ -89,6 +89,24 @@ __device__ __forceinline__ float div_(float a, float b) { return __fdiv_rn(a, b)
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return v < lo ? lo : (hi < v ? hi : v); }  // raymarch_shared.h:104-107
 __device__ __forceinline__ float calc_dt(float t, float cone) { return clampf(mul_(t, cone), MIN_CONE_STEPSIZE(), MAX_CONE_STEPSIZE()); }  // ray_sampler_header.h:24-25
 
+// floor() of |p| < 2^22 and its integer value on the FMA/ALU pipes (F2I / FRND / I2F are quarter-rate XU ops on sm_100):
+// t = p + 1.5*2^23 rounds p to the nearest integer into the low mantissa bits; one compare turns round-to-nearest into floor. Exact.
+__device__ __forceinline__ float floor_small(float p, int *ip) {
+    float t = __fadd_rn(p, 12582912.0f);
+    float r = __fadd_rn(t, -12582912.0f);
+    int i = __float_as_int(t) - 0x4B400000;
+    if (r > p) { r = __fadd_rn(r, -1.0f); i -= 1; }
+    *ip = i;
+    return r;
+}
+// expand_bits() of raymarch_shared.h:753-760 for 7-bit inputs via the identity spread3(v) = sum of bit b moved to 3b: same value, 2 steps
+__device__ __forceinline__ uint32_t expand_bits7(uint32_t v) {
+    v = (v | (v << 8)) & 0x0000F00Fu;   // bits 0-3 stay, bits 4-6 -> 12-14
+    v = (v | (v << 4)) & 0x000C30C3u;   // pairs apart
+    v = (v | (v << 2)) & 0x00249249u;   // every third bit
+    return v;
+}
+
 // frexpf exponent for finite positive normal/zero inputs (the only ones the march produces); matches frexpf incl. 0 -> 0
 __device__ __forceinline__ int frexp_exponent(float v) {
     // v >= 0 finite. Normal numbers: biased exponent - 126 (frexpf's convention 0.5 <= m < 1); zero -> 0; denormals take libm.
@@ -115,10 +133,12 @@ __device__ __forceinline__ uint32_t cascaded_grid_idx_at(float px, float py, flo
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float v = add_(mul_(sub_(q[k], 0.5f), s), 0.5f);
-        int i = (int)mul_(v, (float)NERF_GRIDSIZE);  // trunc toward zero, like the reference's cast<int>()
+        // the reference truncates toward zero (cast<int>) then clamps to [0,127]; floor differs from trunc only for negative values,
+        // which both clamp to 0 -> identical cell. floor_small keeps this off the XU pipe.
+        int i; floor_small(mul_(v, (float)NERF_GRIDSIZE), &i);
         c[k] = (uint32_t)min(max(i, 0), (int)NERF_GRIDSIZE - 1);
     }
-    return morton3D(c[0], c[1], c[2]);
+    return expand_bits7(c[0]) | (expand_bits7(c[1]) << 1) | (expand_bits7(c[2]) << 2);
 }
 __device__ __forceinline__ bool occupied_at(float px, float py, float pz, const uint8_t *__restrict__ bitfield, uint32_t mip) {  // :315-319
     uint32_t idx = cascaded_grid_idx_at(px, py, pz, mip);
@@ -130,7 +150,8 @@ __device__ __forceinline__ float distance_to_next_voxel(const float p[3], const 
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         float pr = mul_((float)res, p[k]);
-        t3[k] = mul_(sub_(floorf(add_(add_(pr, 0.5f), mul_(0.5f, signf_(d[k])))), pr), idir[k]);
+        int unused; float fl = floor_small(add_(add_(pr, 0.5f), mul_(0.5f, signf_(d[k]))), &unused);   // == floorf, |arg| < 2^22
+        t3[k] = mul_(sub_(fl, pr), idir[k]);
     }
     float t = fminf(fminf(t3[0], t3[1]), t3[2]);
     return fmaxf(mul_(t, __uint_as_float((254u - (__float_as_uint((float)res) >> 23)) << 23)), 0.0f);  // t / res, res = 2^k: exact reciprocal, same bits as the division

@@ -225,8 +225,9 @@ __global__ void __launch_bounds__(BW_THREADS) ngp_field_bwd_kernel(HashGridDev g
                 float2 *tl = reinterpret_cast<float2 *>(d_table) + g.offset[l];
                 const float sc = g.scale[l];
                 float qx = __fmaf_rn(sc, px, 0.5f), qy = __fmaf_rn(sc, py, 0.5f), qz = __fmaf_rn(sc, pz, 0.5f);
-                uint32_t ix, iy, iz;
-                float fx = floor_small(qx, &ix), fy = floor_small(qy, &iy), fz = floor_small(qz, &iz);
+                int ixs, iys, izs;
+                float fx = floor_small(qx, &ixs), fy = floor_small(qy, &iys), fz = floor_small(qz, &izs);
+                const uint32_t ix = (uint32_t)ixs, iy = (uint32_t)iys, iz = (uint32_t)izs;
                 fx = qx - fx; fy = qy - fy; fz = qz - fz;
                 const float g0 = gx[2 * l], g1 = gx[2 * l + 1];
 #pragma unroll

@@ -65,25 +65,15 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t 
     return index >= hashmap_size ? index - hashmap_size : index;
 }
 
-// floor() of 0 <= p < 2^22 and its integer value on the FMA/ALU pipes (F2I / FRND / I2F are quarter-rate XU ops):
-// t = p + 1.5*2^23 rounds p to the nearest integer into the low mantissa bits; one compare fixes round-up to floor. Exact.
-__device__ __forceinline__ float floor_small(float p, uint32_t *ip) {
-    float t = __fadd_rn(p, 12582912.0f);
-    float r = __fadd_rn(t, -12582912.0f);
-    int i = __float_as_int(t) - 0x4B400000;
-    if (r > p) { r = __fadd_rn(r, -1.0f); i -= 1; }
-    *ip = (uint32_t)i;
-    return r;
-}
-
 // one level of the multiresolution hash encoding: returns the two interpolated features (fp32, NOT yet rounded)
 __device__ __forceinline__ float2 hash_level(const __half2 *__restrict__ table, const HashGridDev &g, int l, float x, float y, float z) {
     const uint32_t hs = g.offset[l + 1] - g.offset[l], res = g.res[l];
     const __half2 *tl = table + g.offset[l];
     const float sc = g.scale[l];
     float px = __fmaf_rn(sc, x, 0.5f), py = __fmaf_rn(sc, y, 0.5f), pz = __fmaf_rn(sc, z, 0.5f);
-    uint32_t gx, gy, gz;
-    float fx = floor_small(px, &gx), fy = floor_small(py, &gy), fz = floor_small(pz, &gz);
+    int ix_, iy_, iz_;
+    float fx = floor_small(px, &ix_), fy = floor_small(py, &iy_), fz = floor_small(pz, &iz_);
+    const uint32_t gx = (uint32_t)ix_, gy = (uint32_t)iy_, gz = (uint32_t)iz_;
     fx = px - fx; fy = py - fy; fz = pz - fz;
     __half2 v[8];
 #pragma unroll

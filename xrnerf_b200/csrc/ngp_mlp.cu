@@ -145,8 +145,9 @@ __global__ void __launch_bounds__(128) mlp_forward_simt_kernel(const __half *__r
 constexpr int TC_WG = 2;                 // warpgroups (= concurrent 128-sample tiles) per CTA
 constexpr uint32_t TC_TMEM_COLS = 128;   // 64 fp32 accumulator columns per warpgroup
 
-template <bool DENSITY_ONLY>
-__global__ void __launch_bounds__(128 * TC_WG, 2) ngp_field_tc_kernel(HashGridDev g, const __half2 *__restrict__ table, const void *__restrict__ weight_image, uint32_t image_bytes,
+// MAXREG: 128 -> 2 CTAs/SM (16 warps); 80 -> 3 CTAs/SM (24 warps, ~70 B of spills): the gather is latency-bound, occupancy wins
+template <bool DENSITY_ONLY, int MAXREG>
+__global__ void __maxnreg__(MAXREG) ngp_field_tc_kernel(HashGridDev g, const __half2 *__restrict__ table, const void *__restrict__ weight_image, uint32_t image_bytes,
                                                                       int density_hidden, int color_hidden, const float *__restrict__ pts, int pts_stride,
                                                                       const float *__restrict__ dirs, int dirs_stride, int n, const int32_t *__restrict__ n_dev, float *__restrict__ out) {
     extern __shared__ uint8_t dyn_smem[];
@@ -273,14 +274,21 @@ int launch_field(const xrb_ngp_config *cfg, const void *table, const void *dens,
     } else {
         uint32_t image_bytes = weight_image_layout(cfg->density_hidden, cfg->color_hidden).total;
         size_t smem = tc_cta_smem_bytes<TC_WG>(image_bytes);
-        const void *k = density_only ? (const void *)ngp_field_tc_kernel<true> : (const void *)ngp_field_tc_kernel<false>;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // register budget of the field kernel: 128 -> 2 CTAs/SM using the whole register file; 96 -> 2 CTAs/SM leaving 16K registers per SM
+        // for the (latency-bound, 36-register) march kernel of the NEXT batch to co-reside on another stream; 80 -> 3 CTAs/SM.
+        static const int variant = getenv("XRB_TC_REGS") ? atoi(getenv("XRB_TC_REGS")) : 96;
+        const int regs = variant == 128 ? 128 : (variant == 80 ? 80 : 96);
         int n_tiles = (n + 127) / 128;
-        int grid = persistent_grid(k, 128 * TC_WG, smem, (n_tiles + TC_WG - 1) / TC_WG, 2);
-        if (density_only)
-            ngp_field_tc_kernel<true><<<grid, 128 * TC_WG, smem, s>>>(g, (const __half2 *)table, image, image_bytes, cfg->density_hidden, cfg->color_hidden, pts, pts_stride, dirs, dirs_stride, n, n_dev, out);
-        else
-            ngp_field_tc_kernel<false><<<grid, 128 * TC_WG, smem, s>>>(g, (const __half2 *)table, image, image_bytes, cfg->density_hidden, cfg->color_hidden, pts, pts_stride, dirs, dirs_stride, n, n_dev, out);
+#define XRB_LAUNCH_TC(D, R)                                                                                                                         \
+    do {                                                                                                                                            \
+        auto k = ngp_field_tc_kernel<D, R>;                                                                                                         \
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                                            \
+        int grid = persistent_grid((const void *)k, 128 * TC_WG, smem, (n_tiles + TC_WG - 1) / TC_WG, R == 80 ? 3 : 2);                             \
+        k<<<grid, 128 * TC_WG, smem, s>>>(g, (const __half2 *)table, image, image_bytes, cfg->density_hidden, cfg->color_hidden, pts, pts_stride, dirs, dirs_stride, n, n_dev, out); \
+    } while (0)
+        if (density_only) { if (regs == 128) XRB_LAUNCH_TC(true, 128); else if (regs == 96) XRB_LAUNCH_TC(true, 96); else XRB_LAUNCH_TC(true, 80); }
+        else { if (regs == 128) XRB_LAUNCH_TC(false, 128); else if (regs == 96) XRB_LAUNCH_TC(false, 96); else XRB_LAUNCH_TC(false, 80); }
+#undef XRB_LAUNCH_TC
     }
     return check_launch(density_only ? "ngp_density_forward" : "ngp_mlp_forward");
 }

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace xrb {
 
@@ -54,6 +55,14 @@ __device__ __forceinline__ uint32_t march_ray(const float o[3], const float d[3]
 }
 
 constexpr int MARCH_BLOCK = 128;
+// grid for warp-per-ray kernels with persistent (ray-strided) warps
+static inline int warp_grid(int n_rays) { size_t b = ((size_t)n_rays * 32 + 255) / 256, cap = (size_t)NUM_SMS * 8; return (int)(b < cap ? (b ? b : 1) : cap); }
+// The march is a long, divergent, latency-bound chain per ray (ncu r01: kernel time == the slowest warp's serialised union of 32
+// rays' paths). Only every LANE_STRIDE-th lane owns a ray: 4x more warps (the SMs have the slots: 14 -> 55 warps/SM at 65 536 rays),
+// each serialising 8 rays instead of 32.
+constexpr int MAX_LANE_STRIDE = 4;
+constexpr int MARCH_RAYS_PER_BLOCK_MIN = MARCH_BLOCK / MAX_LANE_STRIDE;
+static int lane_stride() { static int v = -1; if (v < 0) { const char *e = getenv("XRB_MARCH_LANE_STRIDE"); v = e ? atoi(e) : 1; if (v != 1 && v != 2 && v != 4) v = 1; } return v; }
 
 struct MarchWs {  // device workspace layout for N rays
     uint32_t *local_excl;  // [N]
@@ -63,11 +72,11 @@ struct MarchWs {  // device workspace layout for N rays
     float *tbuf;           // [N][TCAP] sample t values found by the count pass
 };
 __host__ __device__ inline size_t march_ws_bytes(int n) {
-    size_t nb = (size_t)(n + MARCH_BLOCK - 1) / MARCH_BLOCK;
+    size_t nb = (size_t)(n + MARCH_RAYS_PER_BLOCK_MIN - 1) / MARCH_RAYS_PER_BLOCK_MIN;
     return sizeof(uint32_t) * ((size_t)n * 2 + nb + 16 + (size_t)n * TCAP);
 }
 inline MarchWs march_ws(void *ws, int n) {
-    size_t nb = (size_t)(n + MARCH_BLOCK - 1) / MARCH_BLOCK;
+    size_t nb = (size_t)(n + MARCH_RAYS_PER_BLOCK_MIN - 1) / MARCH_RAYS_PER_BLOCK_MIN;
     MarchWs w; w.local_excl = (uint32_t *)ws; w.startt = (float *)(w.local_excl + n); w.block_sum = (uint32_t *)(w.startt + n); w.misc = w.block_sum + nb; w.tbuf = (float *)(w.misc + 16);
     return w;
 }
@@ -86,13 +95,16 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total)
     return off + incl - v;
 }
 
+template <int LANE_STRIDE>
 __global__ void __launch_bounds__(MARCH_BLOCK) march_count_kernel(int n_rays, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
                                                                   const uint8_t *__restrict__ bitfield, float lo, float hi, float near_distance, float cone,
                                                                   Pcg32 rng, uint32_t *__restrict__ local_excl, float *__restrict__ startt_out,
                                                                   uint32_t *__restrict__ block_sum, int32_t *__restrict__ numsteps, float *__restrict__ tbuf) {
-    uint32_t i = blockIdx.x * MARCH_BLOCK + threadIdx.x;
+    constexpr int MARCH_RAYS_PER_BLOCK = MARCH_BLOCK / LANE_STRIDE;
+    const bool owner = (threadIdx.x % LANE_STRIDE) == 0;
+    uint32_t i = blockIdx.x * MARCH_RAYS_PER_BLOCK + threadIdx.x / LANE_STRIDE;
     uint32_t n = 0;
-    if (i < (uint32_t)n_rays) {
+    if (owner && i < (uint32_t)n_rays) {
         float o[3] = {rays_o[3 * (size_t)i], rays_o[3 * (size_t)i + 1], rays_o[3 * (size_t)i + 2]};
         float d[3] = {rays_d[3 * (size_t)i], rays_d[3 * (size_t)i + 1], rays_d[3 * (size_t)i + 2]};
         float st = ray_start_t(rng, i, lo, hi, o, d, near_distance, cone);
@@ -102,7 +114,7 @@ __global__ void __launch_bounds__(MARCH_BLOCK) march_count_kernel(int n_rays, co
     }
     uint32_t tot;
     uint32_t ex = block_excl_scan(n, &tot);
-    if (i < (uint32_t)n_rays) local_excl[i] = ex;
+    if (owner && i < (uint32_t)n_rays) local_excl[i] = ex;
     if (threadIdx.x == 0) block_sum[blockIdx.x] = tot;
 }
 
@@ -141,18 +153,18 @@ __global__ void __launch_bounds__(256) march_emit_kernel(int n_rays, const float
                                                          float hi, float cone, uint32_t max_samples, const uint32_t *__restrict__ local_excl, const float *__restrict__ startt,
                                                          const uint32_t *__restrict__ block_off, const uint32_t *__restrict__ misc, const float *__restrict__ tbuf,
                                                          float *__restrict__ coords_out, int32_t *__restrict__ rays_index, int32_t *__restrict__ numsteps,
-                                                         int32_t *__restrict__ counters) {
+                                                         int32_t *__restrict__ counters, int rays_per_scan_block) {
     const int lane = threadIdx.x & 31;
-    const uint32_t i = (blockIdx.x * 256 + threadIdx.x) >> 5;
-    bool ok = false;
-    if (i < (uint32_t)n_rays) {
+    const uint32_t n_warps = (gridDim.x * 256) >> 5;
+    uint32_t ok_count = 0;
+    for (uint32_t i = (blockIdx.x * 256 + threadIdx.x) >> 5; i < (uint32_t)n_rays; i += n_warps) {   // persistent warps: 8192 tiny blocks cost more to schedule than to run
         uint32_t n = (uint32_t)numsteps[2 * (size_t)i];
-        uint32_t base = misc[0] + block_off[i / MARCH_BLOCK] + local_excl[i];
+        uint32_t base = misc[0] + block_off[i / rays_per_scan_block] + local_excl[i];
         __syncwarp();
         if (base + n > max_samples) {  // ray_sampler.cu:76-82
             if (lane == 0) { numsteps[2 * (size_t)i] = 0; numsteps[2 * (size_t)i + 1] = (int32_t)base; }
         } else {
-            ok = lane == 0;
+            ok_count += 1;
             if (lane == 0) {
                 numsteps[2 * (size_t)i + 1] = (int32_t)base;
                 // serial-order equivalent of `ray_idx = atomicAdd(ray_counter,1)`: slots are a prefix of the rays
@@ -171,14 +183,24 @@ __global__ void __launch_bounds__(256) march_emit_kernel(int n_rays, const float
                         c[3] = warp_dt(calc_dt(t, cone));
                         c[4] = w0; c[5] = w1; c[6] = w2;
                     }
-                } else if (lane == 0) {
-                    march_ray<true>(o, d, lo, hi, startt[i], cone, bitfield, n, coords_out + 7 * (size_t)base);
+                } else {
+                    // long ray: lanes rebuild the first TCAP-1 rows from the cache; lane 0 resumes the march AT cached sample TCAP-1
+                    // (the march state is just t) and emits the remaining n-(TCAP-1) rows
+                    const float diag = sub_(hi, lo);
+                    const float w0 = mul_(add_(d[0], 1.0f), 0.5f), w1 = mul_(add_(d[1], 1.0f), 0.5f), w2 = mul_(add_(d[2], 1.0f), 0.5f);
+                    for (uint32_t j = lane; j < TCAP - 1; j += 32) {
+                        float t = tbuf[(size_t)i * TCAP + j];
+                        float *c = coords_out + 7 * (size_t)(base + j);
+                        c[0] = div_(sub_(add_(o[0], mul_(t, d[0])), lo), diag); c[1] = div_(sub_(add_(o[1], mul_(t, d[1])), lo), diag); c[2] = div_(sub_(add_(o[2], mul_(t, d[2])), lo), diag);
+                        c[3] = warp_dt(calc_dt(t, cone));
+                        c[4] = w0; c[5] = w1; c[6] = w2;
+                    }
+                    if (lane == 0) march_ray<true>(o, d, lo, hi, tbuf[(size_t)i * TCAP + TCAP - 1], cone, bitfield, n - (TCAP - 1), coords_out + 7 * (size_t)(base + TCAP - 1));
                 }
             }
         }
     }
-    uint32_t cnt = __syncthreads_count(ok);
-    if (threadIdx.x == 0 && cnt && counters) atomicAdd((unsigned int *)counters, cnt);
+    if (lane == 0 && ok_count && counters) atomicAdd((unsigned int *)counters, ok_count);
 }
 
 // ============================================================================ compaction (compacted_coord.cu:5-77)
@@ -232,14 +254,14 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(int n_rays, const fl
                                                             const int32_t *__restrict__ numsteps_c, const float *__restrict__ bg, float3 bg_global, int rgb_act, int dens_act,
                                                             float *__restrict__ rgb_out, float *__restrict__ alpha_out) {
     int lane = threadIdx.x & 31;
-    uint32_t ray = (blockIdx.x * 256 + threadIdx.x) >> 5;
-    if (ray >= (uint32_t)n_rays) return;
+    const uint32_t n_warps = (gridDim.x * 256) >> 5;
+    for (uint32_t ray = (blockIdx.x * 256 + threadIdx.x) >> 5; ray < (uint32_t)n_rays; ray += n_warps) {
     const int32_t *ns = MODE == 0 ? numsteps_c : numsteps;
     uint32_t n = (uint32_t)ns[2 * (size_t)ray], base = (uint32_t)ns[2 * (size_t)ray + 1];
     float3 b = MODE == 0 ? make_float3(bg[3 * (size_t)ray], bg[3 * (size_t)ray + 1], bg[3 * (size_t)ray + 2]) : bg_global;
     if (n == 0) {
         if (lane == 0) { rgb_out[3 * (size_t)ray] = b.x; rgb_out[3 * (size_t)ray + 1] = b.y; rgb_out[3 * (size_t)ray + 2] = b.z; if (MODE == 1) alpha_out[ray] = 0.f; }
-        return;
+        continue;
     }
     float T = 1.f, ax = 0.f, ay = 0.f, az = 0.f;
     for (uint32_t k0 = 0; k0 < n; k0 += 32) {
@@ -264,6 +286,7 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(int n_rays, const fl
         rgb_out[3 * (size_t)ray] = ax; rgb_out[3 * (size_t)ray + 1] = ay; rgb_out[3 * (size_t)ray + 2] = az;
         if (MODE == 1) alpha_out[ray] = 1.f - T;
     }
+    }
 }
 
 // compute_rgbs_grad (calc_rgb.cu:70-140)
@@ -271,10 +294,10 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(int n_rays, const fl
                                                             const float *__restrict__ grad_rgb, const float *__restrict__ rgb_final, const float *__restrict__ grid_mean,
                                                             int rgb_act, int dens_act, float4 *__restrict__ dl_draw) {
     int lane = threadIdx.x & 31;
-    uint32_t ray = (blockIdx.x * 256 + threadIdx.x) >> 5;
-    if (ray >= (uint32_t)n_rays) return;
+    const uint32_t n_warps = (gridDim.x * 256) >> 5;
+    for (uint32_t ray = (blockIdx.x * 256 + threadIdx.x) >> 5; ray < (uint32_t)n_rays; ray += n_warps) {
     uint32_t n = (uint32_t)numsteps_c[2 * (size_t)ray], base = (uint32_t)numsteps_c[2 * (size_t)ray + 1];
-    if (n == 0) return;
+    if (n == 0) continue;
     float loss_scale = 128.f / (float)n_rays;                                         // :92-93
     const float l2 = rgb_act == XRB_ACT_EXPONENTIAL ? 1e-4f : 0.0f;                   // :103
     const float l1 = __ldg(grid_mean) < NERF_MIN_OPTICAL_THICKNESS ? 1e-4f : 0.0f;    // :104
@@ -304,6 +327,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(int n_rays, const fl
         }
         T *= __shfl_sync(0xffffffffu, incl, 31);
         px = __shfl_sync(0xffffffffu, sx, 31); py = __shfl_sync(0xffffffffu, sy, 31); pz = __shfl_sync(0xffffffffu, sz, 31);
+    }
     }
 }
 
@@ -470,12 +494,15 @@ int xrb_rm_rays_sampler(const float *rays_o, const float *rays_d, const uint8_t 
     XRB_REQUIRE(rays_o && rays_d && bitfield && coords_out && rays_index && numsteps && counters && workspace, "rays_sampler: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     MarchWs w = march_ws(workspace, n_rays);
-    int nb = (n_rays + MARCH_BLOCK - 1) / MARCH_BLOCK;
+    const int ls = lane_stride(), rpb = MARCH_BLOCK / ls;
+    int nb = (n_rays + rpb - 1) / rpb;
     Pcg32 rng = host_rng(seed, n_prior_calls);
-    march_count_kernel<<<nb, MARCH_BLOCK, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, near_distance, cone_angle, rng, w.local_excl, w.startt, w.block_sum, numsteps, w.tbuf);
+    if (ls == 1) march_count_kernel<1><<<nb, MARCH_BLOCK, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, near_distance, cone_angle, rng, w.local_excl, w.startt, w.block_sum, numsteps, w.tbuf);
+    else if (ls == 2) march_count_kernel<2><<<nb, MARCH_BLOCK, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, near_distance, cone_angle, rng, w.local_excl, w.startt, w.block_sum, numsteps, w.tbuf);
+    else march_count_kernel<4><<<nb, MARCH_BLOCK, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, near_distance, cone_angle, rng, w.local_excl, w.startt, w.block_sum, numsteps, w.tbuf);
     march_scan_kernel<<<1, 1024, 0, s>>>(nb, w.block_sum, w.misc, counters);
-    march_emit_kernel<<<(int)(((size_t)n_rays * 32 + 255) / 256), 256, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, cone_angle, (uint32_t)max_samples, w.local_excl, w.startt,
-                                                                             w.block_sum, w.misc, w.tbuf, coords_out, rays_index, numsteps, counters);
+    march_emit_kernel<<<warp_grid(n_rays), 256, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, cone_angle, (uint32_t)max_samples, w.local_excl, w.startt,
+                                                                             w.block_sum, w.misc, w.tbuf, coords_out, rays_index, numsteps, counters, rpb);
     return check_launch("rays_sampler");
 }
 
@@ -509,7 +536,7 @@ int xrb_rm_calc_rgb_forward(const float *raw, const float *coords, const int32_t
     if (n_rays == 0) return XRB_OK;
     XRB_REQUIRE(raw && coords && numsteps && numsteps_compacted && bg && rgb_out, "calc_rgb_forward: null pointer");
     XRB_REQUIRE(((uintptr_t)raw & 15) == 0, "calc_rgb_forward: raw must be 16-byte aligned");
-    int blocks = (int)(((size_t)n_rays * 32 + 255) / 256);
+    int blocks = warp_grid(n_rays);
     composite_fwd_kernel<0><<<blocks, 256, 0, (cudaStream_t)stream>>>(n_rays, (const float4 *)raw, coords, numsteps, numsteps_compacted, bg, make_float3(0, 0, 0), rgb_act, dens_act,
                                                                       rgb_out, nullptr);
     return check_launch("calc_rgb_forward");
@@ -521,7 +548,7 @@ int xrb_rm_calc_rgb_backward(const float *raw, const int32_t *numsteps_compacted
     if (n_rays == 0) return XRB_OK;
     XRB_REQUIRE(raw && coords && numsteps_compacted && grad_rgb && rgb && grid_mean && dl_draw, "calc_rgb_backward: null pointer");
     XRB_REQUIRE(((uintptr_t)raw & 15) == 0 && ((uintptr_t)dl_draw & 15) == 0, "calc_rgb_backward: raw/dl_draw must be 16-byte aligned");
-    int blocks = (int)(((size_t)n_rays * 32 + 255) / 256);
+    int blocks = warp_grid(n_rays);
     composite_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n_rays, (const float4 *)raw, coords, numsteps_compacted, grad_rgb, rgb, grid_mean, rgb_act, dens_act,
                                                                    (float4 *)dl_draw);
     return check_launch("calc_rgb_backward");
@@ -533,7 +560,7 @@ int xrb_rm_calc_rgb_inference(const float *raw, const float *coords, const int32
     if (n_rays == 0) return XRB_OK;
     XRB_REQUIRE(raw && coords && numsteps && bg3_host && rgb_out && alpha_out, "calc_rgb_inference: null pointer");
     XRB_REQUIRE(((uintptr_t)raw & 15) == 0, "calc_rgb_inference: raw must be 16-byte aligned");
-    int blocks = (int)(((size_t)n_rays * 32 + 255) / 256);
+    int blocks = warp_grid(n_rays);
     composite_fwd_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(n_rays, (const float4 *)raw, coords, numsteps, nullptr, nullptr,
                                                                       make_float3(bg3_host[0], bg3_host[1], bg3_host[2]), rgb_act, dens_act, rgb_out, alpha_out);
     return check_launch("calc_rgb_inference");
