@@ -271,6 +271,28 @@ def run_ours(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
 
+    # ---- training arm (fwd + bwd + all-reduce + Adam per step; device-resident batches; same rays, synthetic targets)
+    train = None
+    if not args.no_train:
+        from xrnerf_b200.train import NgpTrainer
+        tr = NgpTrainer(field, bf, N_RAYS)
+        tgt = torch.rand((N_RAYS, 3), device=dev); bgc = torch.zeros((N_RAYS, 3), device=dev)
+        for i in range(max(W, 3)):
+            tr.step(*dev_batches[i % N_BATCHES], tgt, bgc)
+        barrier()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        for i in range(K):
+            tr.step(*dev_batches[(W + i) % N_BATCHES], tgt, bgc)
+        t1e.record()
+        barrier()
+        tm = torch.tensor([t0e.elapsed_time(t1e)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        train = {'value': world * N_RAYS * K / (float(tm.item()) * 1e-3), 'unit': 'rays/s', 'ms_per_step': float(tm.item()) / K,
+                 'what': 'march + compaction + field fwd (tcgen05) + composite fwd/bwd + field bwd + grad all-reduce (NCCL, world>1) + fused Adam over 12.2M params',
+                 'compacted_samples_per_step': int(tr.cnt_c[1].item())}
+
     if rank == 0:
         peak, peak_src = peaks()
         f_ms = float(np.mean(field_ms))
@@ -292,6 +314,7 @@ def run_ours(args):
                          'algorithmic_bytes_per_launch': s_mean * BYTES_PER_SAMPLE,
                          'note': 'hash table (24.4 MB fp16) is L2-resident by design; traffic (dram bytes) comes from the ncu capture in profiles/'},
             'cpu_baseline': {'value': cpu_rate, 'unit': 'rays/s', 'cores': cores, 'kind': kind, 'sample': sample},
+            'train': train,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -304,7 +327,8 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--pipeline', type=int, default=2, help='ray batches in flight (CUDA streams); 1 = strictly sequential steps')
+    ap.add_argument('--no-train', dest='no_train', action='store_true', help='skip the training arm')
+    ap.add_argument('--pipeline', type=int, default=4, help='ray batches in flight (CUDA streams); 1 = strictly sequential steps')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
