@@ -207,6 +207,11 @@ int xrb_nerf_sample_pdf(const float *z_vals, const float *weights, const float *
 int xrb_nerf_posenc(const float *pts, const float *viewdirs, int64_t n_pts, int samples_per_ray, int multires, int multires_dirs,
                     float *embedded, void *stream);
 
+/* NerfMLP.run_mlp (xrnerf/models/mlps/nerf_mlp.py:70-94; netdepth 8, netwidth 256, skips [4], use_viewdirs) as one persistent tcgen05
+ * kernel, inference forward. embedded f32[n, input_ch + input_ch_dirs] ((63,27) NeRF or (96,27) Mip-NeRF) -> raw f32[n,4] = (rgb3, alpha1).
+ * weight_image / bias: produced by xrnerf_b200.nerf_mlp.pack_nerf_mlp (fp16 slabs, K-major, 128-byte swizzle, in streaming order). */
+int xrb_nerf_mlp_forward(const void *weight_image, const float *bias, const float *embedded, int64_t n_rows, int input_ch, int input_ch_dirs, float *raw, void *stream);
+
 /* Mip-NeRF cast_rays + MipNerfEmbedder.forward (networks/utils/mip.py:66-129, embedders/mipnerf_embedder.py:43-99, cone, diag):
  * z_vals f32[N,S+1], radii f32[N] -> embedded f32[N*S, 6*(max_deg_point-min_deg_point) + 3 + 6*(max_deg_view-min_deg_view)];
  * means_out/covs_out f32[N,S,3] optional (both or neither). */

@@ -1,0 +1,87 @@
+"""GPU parity of the fused tcgen05 NerfMLP kernel (xrb_nerf_mlp_forward) against the fp32 path of the same module (library GEMMs, the
+reference's arithmetic) and the numpy oracle. Tolerance for the fp16-operand / fp32-accumulate pipeline over 12 layers:
+|err| <= 2e-2 * max|raw| (measured ~3e-3); composited rgb <= 5e-3."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+NERF_MLP = dict(type='NerfMLP', skips=[4], netdepth=8, netwidth=256, netchunk=1024 * 32, output_ch=5, use_viewdirs=True,
+                embedder=dict(type='BaseEmbedder', i_embed=0, multires=10, multires_dirs=4))
+MIP_MLP = dict(type='NerfMLP', skips=[4], netdepth=8, netwidth=256, netchunk=1024 * 32, use_viewdirs=True,
+               embedder=dict(type='MipNerfEmbedder', min_deg_point=0, max_deg_point=16, min_deg_view=0, max_deg_view=4, use_viewdirs=True, append_identity=True))
+
+
+def _ref_fp32(mlp, emb):
+    with torch.enable_grad():   # autograd on => library-GEMM fp32 path
+        return mlp.batchify_run_mlp(emb.clone().requires_grad_(True)).detach()
+
+
+@pytest.mark.parametrize('n_rays,s', [(1, 1), (1, 127), (3, 43), (40, 64), (500, 192)])
+def test_fused_nerf_mlp_matches_fp32_path(n_rays, s):
+    from xrnerf_b200 import registry as R
+    torch.manual_seed(0)
+    mlp = R.build_mlp(NERF_MLP).cuda()
+    pts = torch.rand((n_rays, s, 3), device='cuda') * 4 - 2
+    vd = torch.nn.functional.normalize(torch.randn((n_rays, 3), device='cuda'), dim=-1)
+    with torch.no_grad():
+        data = mlp({'pts': pts, 'viewdirs': vd})
+        emb = mlp.embedder({'pts': pts, 'viewdirs': vd})['embedded']
+    raw = data['raw']
+    assert raw.shape == (n_rays, s, 4) and torch.isfinite(raw).all()
+    ref = _ref_fp32(mlp, emb).reshape(n_rays, s, 4)
+    err = (raw - ref).abs().max().item()
+    assert err <= 2e-2 * ref.abs().max().item() + 1e-3, err
+
+
+def test_fused_nerf_mlp_vs_numpy_oracle_and_render():
+    from oracle import nerf_oracle as O
+    from xrnerf_b200 import registry as R
+    torch.manual_seed(1)
+    mlp = R.build_mlp(NERF_MLP).cuda()
+    render = R.build_render(dict(type='NerfRender', white_bkgd=True, raw_noise_std=0))
+    rng = np.random.default_rng(0)
+    n, s = 64, 64
+    o = (rng.random((n, 3)) * 0.2).astype(np.float32); d = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    vd = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    z = np.broadcast_to(np.linspace(2, 6, s, dtype=np.float32), (n, s)).copy()
+    pts = o[:, None] + d[:, None] * z[..., None]
+    sd = {k: v.detach().cpu().numpy() for k, v in mlp.state_dict().items()}
+    raw_ref = O.nerf_mlp(sd, O.embed(pts, vd), 63, 27).reshape(n, s, 4)
+    rgb_ref = O.nerf_render(raw_ref, z, d, white_bkgd=True)['rgb']
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    with torch.no_grad():
+        data = mlp({'pts': t(pts), 'viewdirs': t(vd)})
+        data.update(z_vals=t(z), rays_d=t(d))
+        _, ret = render(data, is_test=True)
+    assert np.abs(data['raw'].cpu().numpy() - raw_ref).max() <= 2e-2 * np.abs(raw_ref).max() + 1e-3
+    assert np.abs(ret['rgb'].cpu().numpy() - rgb_ref).max() <= 5e-3
+
+
+def test_fused_mip_mlp_matches_fp32_path():
+    from xrnerf_b200 import registry as R
+    torch.manual_seed(2)
+    mlp = R.build_mlp(MIP_MLP).cuda()
+    n, s1 = 300, 129
+    d = torch.randn((n, 3), device='cuda')
+    data = dict(rays_o=torch.rand((n, 3), device='cuda') * 0.2, rays_d=d, viewdirs=torch.nn.functional.normalize(d, dim=-1), radii=torch.full((n, 1), 1e-3, device='cuda'),
+                z_vals=torch.linspace(2, 6, s1, device='cuda').expand(n, s1).contiguous())
+    with torch.no_grad():
+        emb = mlp.embedder(dict(data))['embedded']
+        raw = mlp(dict(data))['raw']
+    assert raw.shape == (n, s1 - 1, 4)
+    ref = _ref_fp32(mlp, emb).reshape(n, s1 - 1, 4)
+    assert (raw - ref).abs().max().item() <= 2e-2 * ref.abs().max().item() + 1e-3
+
+
+def test_weight_repack_on_update():
+    from xrnerf_b200 import registry as R
+    torch.manual_seed(3)
+    mlp = R.build_mlp(NERF_MLP).cuda()
+    pts = torch.rand((8, 16, 3), device='cuda'); vd = torch.nn.functional.normalize(torch.randn((8, 3), device='cuda'), dim=-1)
+    with torch.no_grad():
+        a = mlp({'pts': pts, 'viewdirs': vd})['raw'].clone()
+        mlp.rgb_linear.bias.add_(1.0)
+        b = mlp({'pts': pts, 'viewdirs': vd})['raw']
+    assert torch.allclose(b[..., :3], a[..., :3] + 1.0, atol=1e-5) and torch.equal(a[..., 3], b[..., 3])

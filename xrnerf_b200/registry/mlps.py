@@ -20,13 +20,13 @@ class NerfMLP(BaseMLP):
     """8x256 ReLU MLP with skip at layer 4 and a 128-wide view branch; parameters are nn.Linear modules with the reference's
     names (pts_linears.i, views_linears.0, feature_linear, alpha_linear, rgb_linear) so reference checkpoints load.
 
-    The dense layers are plain library GEMMs here (cuBLAS through torch, TF32 off = fp32 like the reference's default on
-    torch>=1.12); the embedding before them and the compositing after them are this package's kernels. The tcgen05
-    fused 256-wide chain is the planned replacement."""
+    Inference (no_grad) runs the whole chain in ONE persistent tcgen05 kernel (csrc/nerf_mlp_tc.cu; fp16 operands, fp32 accumulate).
+    With autograd enabled (training) the dense layers are library GEMMs (cuBLAS through torch, fp32) — the tensor-core backward is not
+    written yet."""
 
-    def __init__(self, skips=[4], netdepth=8, netwidth=256, output_ch=4, use_viewdirs=True, netchunk=1024 * 32, embedder=None, **kwarg):
+    def __init__(self, skips=[4], netdepth=8, netwidth=256, output_ch=4, use_viewdirs=True, netchunk=1024 * 32, embedder=None, fused=True, **kwarg):
         super().__init__()
-        self.skips, self.chunk, self.use_viewdirs = skips, netchunk, use_viewdirs
+        self.skips, self.chunk, self.use_viewdirs, self.fused = skips, netchunk, use_viewdirs, fused
         self.embedder = builder.build_embedder(embedder)
         D, W = netdepth, netwidth
         self.input_ch, self.input_ch_dirs = self.embedder.get_embed_ch()
@@ -46,7 +46,23 @@ class NerfMLP(BaseMLP):
         del data['unflatten_shape']
         return data
 
+    def _fused_ok(self, x):
+        return (self.fused and not torch.is_grad_enabled() and x.is_cuda and self.use_viewdirs and len(self.pts_linears) == 8 and list(self.skips) == [4]
+                and self.pts_linears[0].out_features == 256 and (self.input_ch, self.input_ch_dirs) in ((63, 27), (96, 27)))
+
+    def _packed(self):
+        ver = tuple(p._version for p in self.parameters()) + (self.pts_linears[0].weight.device,)
+        if getattr(self, '_pack_ver', None) != ver:
+            from ..nerf_mlp import pack_nerf_mlp
+            self._pack = pack_nerf_mlp(self)
+            self._pack_ver = ver
+        return self._pack
+
     def batchify_run_mlp(self, x):
+        if self._fused_ok(x):   # inference: the whole 12-GEMM chain in one tcgen05 kernel, no chunking needed (activations never leave the SM)
+            from ..nerf_mlp import nerf_mlp_forward
+            image, bias = self._packed()
+            return nerf_mlp_forward(image, bias, x, self.input_ch, self.input_ch_dirs)
         if self.chunk is None:
             return self.run_mlp(x)
         return torch.cat([self.run_mlp(x[i:i + self.chunk]) for i in range(0, x.shape[0], self.chunk)], 0)
