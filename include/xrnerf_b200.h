@@ -211,6 +211,14 @@ int xrb_nerf_posenc(const float *pts, const float *viewdirs, int64_t n_pts, int 
  * kernel, inference forward. embedded f32[n, input_ch + input_ch_dirs] ((63,27) NeRF or (96,27) Mip-NeRF) -> raw f32[n,4] = (rgb3, alpha1).
  * weight_image / bias: produced by xrnerf_b200.nerf_mlp.pack_nerf_mlp (fp16 slabs, K-major, 128-byte swizzle, in streaming order). */
 int xrb_nerf_mlp_forward(const void *weight_image, const float *bias, const float *embedded, int64_t n_rows, int input_ch, int input_ch_dirs, float *raw, void *stream);
+/* v2 of the same kernel: two epilogue warpgroups per tile, phased MMA issue, double-buffered TMEM accumulators, half-slab weight stream
+ * (image/bias from xrnerf_b200.nerf_mlp.pack_nerf_mlp_v2) */
+int xrb_nerf_mlp_forward_v2(const void *weight_image, const float *bias, const void *enc_image, int64_t n_rows, int input_ch, int input_ch_dirs, float *raw, void *stream);
+/* encoding tile image consumed by v2 (per 128-row tile: point-encoding block(s) then direction block, [128x64] fp16, UMMA K-major 128B swizzle):
+ * size, conversion from an fp32 `embedded` matrix, and BaseEmbedder's positional encoding written directly in that form */
+size_t xrb_nerf_enc_image_bytes(int64_t n_rows, int input_ch);
+int xrb_nerf_pack_embedded(const float *embedded, int64_t n_rows, int input_ch, int input_ch_dirs, void *enc_image, void *stream);
+int xrb_nerf_posenc_tiles(const float *pts, const float *viewdirs, int64_t n_pts, int samples_per_ray, int multires, int multires_dirs, void *enc_image, void *stream);
 
 /* Mip-NeRF cast_rays + MipNerfEmbedder.forward (networks/utils/mip.py:66-129, embedders/mipnerf_embedder.py:43-99, cone, diag):
  * z_vals f32[N,S+1], radii f32[N] -> embedded f32[N*S, 6*(max_deg_point-min_deg_point) + 3 + 6*(max_deg_view-min_deg_view)];

@@ -23,10 +23,22 @@ def timeit(fn, n=5, warm=2):
 mlp = R.build_mlp(MLP).cuda()
 rows = 32768 * 64            # 32 768 rays x 64 samples
 emb = torch.randn((rows, 90), device='cuda')
-image, bias = mlp._packed()
-t = timeit(lambda: nerf_mlp_forward(image, bias, emb, 63, 27))
 flop = rows * 593408 * 2
-print(f'fused tcgen05 NerfMLP: {t:.3f} ms for {rows} rows -> {flop / t / 1e9:.1f} TFLOP/s ({rows / t / 1e3:.1f} Mrows/s)')
+from xrnerf_b200.nerf_mlp import pack_nerf_mlp, pack_nerf_mlp_v2
+for v, packer in (((2, pack_nerf_mlp_v2),) if os.environ.get('XRB_NM_DBG') else ((1, pack_nerf_mlp), (2, pack_nerf_mlp_v2))):
+    image, bias = packer(mlp)
+    t = timeit(lambda: nerf_mlp_forward(image, bias, emb, 63, 27, version=v))
+    print(f'fused tcgen05 NerfMLP v{v}: {t:.3f} ms for {rows} rows -> {flop / t / 1e9:.1f} TFLOP/s ({rows / t / 1e3:.1f} Mrows/s)', flush=True)
+    if v == 2:
+        from xrnerf_b200 import _C
+        from xrnerf_b200.nerf_mlp import nerf_mlp_forward_tiles
+        enc = torch.empty(_C.lib.xrb_nerf_enc_image_bytes(rows, 63), dtype=torch.uint8, device='cuda')
+        _C.check(_C.lib.xrb_nerf_pack_embedded(_C.ptr(emb), rows, 63, 27, _C.ptr(enc), _C.stream()))
+        raw = torch.empty((rows, 4), device='cuda')
+        t = timeit(lambda: nerf_mlp_forward_tiles(image, bias, enc, rows, 63, 27, raw))
+        print(f'   v2 MLP kernel alone (pre-packed encodings): {t:.3f} ms -> {flop / t / 1e9:.1f} TFLOP/s', flush=True)
+if os.environ.get('XRB_NM_DBG'):
+    sys.exit(0)
 with torch.enable_grad():
     x = emb[:32768 * 8].clone().requires_grad_(True)
     t2 = timeit(lambda: mlp.batchify_run_mlp(x), n=3, warm=1)

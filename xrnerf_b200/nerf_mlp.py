@@ -74,10 +74,71 @@ def pack_nerf_mlp(mlp):
     return image, bias
 
 
-def nerf_mlp_forward(image, bias, embedded, input_ch, input_ch_dirs):
+def pack_nerf_mlp_v2(mlp):
+    """Image for csrc/nerf_mlp_tc.cu v2: HALF slabs ([N/2 x 64]) in the kernel's MMA issue order
+    S1=(half0; aux+lo blocks) S2=(half1; aux+lo) S3=(half0; hi blocks) S4=(half1; hi); bias vector = per-layer biases, then Wa[256], ba."""
+    assert len(mlp.pts_linears) == 8 and list(mlp.skips) == [4] and mlp.use_viewdirs and mlp.pts_linears[0].out_features == 256
+    ic, icd = mlp.input_ch, mlp.input_ch_dirs
+    aux = (ic + 63) // 64
+    g = lambda lin: (lin.weight.detach().float().cpu().numpy(), lin.bias.detach().float().cpu().numpy())
+    PTS, DIR = 'pts', 'dir'
+
+    def cols(W, kind, j, h_off=0, pts_w=None):
+        """64 weight columns feeding A block (kind, j): hidden block j -> W[:, h_off+64j ..]; pts block j -> pts part; dir -> W[:, 256:]"""
+        if kind == 'h':
+            return _pad_cols(W, h_off + 64 * j, h_off + 64 * (j + 1))
+        if kind == PTS:
+            return _pad_cols(pts_w, 64 * j, 64 * (j + 1))
+        return _pad_cols(W[:, 256:], 0, 64)
+
+    layers = []   # (W_padded_rows [N, ...], first blocks, second blocks, N, n_halves, bias)
+    W, b = g(mlp.pts_linears[0])
+    layers.append((W, [(PTS, j, dict(pts_w=W)) for j in range(aux)], [], 256, 2, b))
+    for l in range(1, 8):
+        W, b = g(mlp.pts_linears[l])
+        if l == 5:
+            first = [(PTS, j, dict(pts_w=W[:, :ic])) for j in range(aux)] + [('h', 0, dict(h_off=ic)), ('h', 1, dict(h_off=ic))]
+            second = [('h', 2, dict(h_off=ic)), ('h', 3, dict(h_off=ic))]
+        else:
+            first, second = [('h', 0, {}), ('h', 1, {})], [('h', 2, {}), ('h', 3, {})]
+        layers.append((W, first, second, 256, 2, b))
+    W, b = g(mlp.feature_linear)
+    layers.append((W, [('h', 0, {}), ('h', 1, {})], [('h', 2, {}), ('h', 3, {})], 256, 2, b))
+    W, b = g(mlp.views_linears[0])
+    layers.append((W, [(DIR, 0, {}), ('h', 0, {}), ('h', 1, {})], [('h', 2, {}), ('h', 3, {})], 128, 2, b))
+    Wr, br = g(mlp.rgb_linear)
+    W16 = np.zeros((16, 128), np.float32); W16[:3] = Wr
+    layers.append((W16, [('h', 0, {})], [('h', 1, {})], 16, 1, np.concatenate([br, np.zeros(13, np.float32)])))
+    slabs, biases = [], []
+    for (W, first, second, N, nh, b) in layers:
+        hw = N // nh
+        for (kind, j, kw) in first + second:        # stream order: per K-block, output half 0 then half 1 (one ring per issuer)
+            for half in range(nh):
+                slabs.append(_slab(cols(W, kind, j, **kw)[half * hw:(half + 1) * hw]))
+        biases.append(b.astype(np.float32))
+    Wa, ba = g(mlp.alpha_linear)
+    biases += [Wa[0].astype(np.float32), ba.astype(np.float32)]
+    dev = mlp.pts_linears[0].weight.device
+    return torch.from_numpy(np.concatenate(slabs)).to(dev), torch.from_numpy(np.concatenate(biases)).to(dev)
+
+
+def nerf_mlp_forward(image, bias, embedded, input_ch, input_ch_dirs, version=1):
     _C.require_cuda(image, bias, embedded)
     embedded = embedded.contiguous().float()
     n = embedded.shape[0]
     raw = torch.empty((n, 4), dtype=torch.float32, device=embedded.device)
-    _C.check(_C.lib.xrb_nerf_mlp_forward(_C.ptr(image), _C.ptr(bias), _C.ptr(embedded), n, int(input_ch), int(input_ch_dirs), _C.ptr(raw), _C.stream()), 'nerf_mlp_forward')
+    if version == 2:   # fp32 embedded -> fp16 tile image (one streaming kernel) -> MLP kernel that TMA-loads it
+        enc = torch.empty(_C.lib.xrb_nerf_enc_image_bytes(n, int(input_ch)), dtype=torch.uint8, device=embedded.device)
+        _C.check(_C.lib.xrb_nerf_pack_embedded(_C.ptr(embedded), n, int(input_ch), int(input_ch_dirs), _C.ptr(enc), _C.stream()), 'nerf_pack_embedded')
+        return nerf_mlp_forward_tiles(image, bias, enc, n, input_ch, input_ch_dirs, raw)
+    fn = _C.lib.xrb_nerf_mlp_forward
+    _C.check(fn(_C.ptr(image), _C.ptr(bias), _C.ptr(embedded), n, int(input_ch), int(input_ch_dirs), _C.ptr(raw), _C.stream()), 'nerf_mlp_forward')
+    return raw
+
+
+def nerf_mlp_forward_tiles(image, bias, enc_image, n_rows, input_ch, input_ch_dirs, raw=None):
+    """v2 kernel on an already packed encoding tile image (xrb_nerf_pack_embedded / xrb_nerf_posenc_tiles)."""
+    if raw is None:
+        raw = torch.empty((n_rows, 4), dtype=torch.float32, device=enc_image.device)
+    _C.check(_C.lib.xrb_nerf_mlp_forward_v2(_C.ptr(image), _C.ptr(bias), _C.ptr(enc_image), n_rows, int(input_ch), int(input_ch_dirs), _C.ptr(raw), _C.stream()), 'nerf_mlp_forward_v2')
     return raw

@@ -51,10 +51,12 @@ class NerfMLP(BaseMLP):
                 and self.pts_linears[0].out_features == 256 and (self.input_ch, self.input_ch_dirs) in ((63, 27), (96, 27)))
 
     def _packed(self):
-        ver = tuple(p._version for p in self.parameters()) + (self.pts_linears[0].weight.device,)
+        import os
+        self.kernel_version = int(os.environ.get('XRB_NERF_MLP_V', '2'))
+        ver = tuple(p._version for p in self.parameters()) + (self.pts_linears[0].weight.device, self.kernel_version)
         if getattr(self, '_pack_ver', None) != ver:
-            from ..nerf_mlp import pack_nerf_mlp
-            self._pack = pack_nerf_mlp(self)
+            from ..nerf_mlp import pack_nerf_mlp, pack_nerf_mlp_v2
+            self._pack = pack_nerf_mlp_v2(self) if self.kernel_version == 2 else pack_nerf_mlp(self)
             self._pack_ver = ver
         return self._pack
 
@@ -62,7 +64,7 @@ class NerfMLP(BaseMLP):
         if self._fused_ok(x):   # inference: the whole 12-GEMM chain in one tcgen05 kernel, no chunking needed (activations never leave the SM)
             from ..nerf_mlp import nerf_mlp_forward
             image, bias = self._packed()
-            return nerf_mlp_forward(image, bias, x, self.input_ch, self.input_ch_dirs)
+            return nerf_mlp_forward(image, bias, x, self.input_ch, self.input_ch_dirs, version=self.kernel_version)
         if self.chunk is None:
             return self.run_mlp(x)
         return torch.cat([self.run_mlp(x[i:i + self.chunk]) for i in range(0, x.shape[0], self.chunk)], 0)
