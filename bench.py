@@ -293,6 +293,43 @@ def run_ours(args):
                  'what': 'march + compaction + field fwd (tcgen05) + composite fwd/bwd + field bwd + grad all-reduce (NCCL, world>1) + fused Adam over 12.2M params',
                  'compacted_samples_per_step': int(tr.cnt_c[1].item())}
 
+    # ---- NeRF arm (BASELINE configs[2]: hierarchical 64 + 128, 800x800-shaped rays): fused tcgen05 NerfMLP path, device-resident rays
+    nerf = None
+    if not args.no_nerf:
+        from xrnerf_b200 import registry as R
+        from xrnerf_b200.nerf import NerfRenderer
+        mlp_cfg = dict(type='NerfMLP', skips=[4], netdepth=8, netwidth=256, netchunk=1024 * 32, output_ch=5, use_viewdirs=True, embedder=dict(type='BaseEmbedder', i_embed=0, multires=10, multires_dirs=4))
+        net = R.build_network(dict(type='NerfNetwork', cfg=dict(phase='test', N_importance=128, is_perturb=False, chunk=1024 * 32, bs_data='rays_o'), mlp=mlp_cfg, mlp_fine=mlp_cfg,
+                                   render=dict(type='NerfRender', white_bkgd=True, raw_noise_std=0))).to(dev)
+        nr = NerfRenderer(net, near=2.0, far=6.0, n_samples=64)
+        n_nerf = 32768
+        ro, rd = dev_batches[0][0][:n_nerf].contiguous(), dev_batches[0][1][:n_nerf].contiguous()
+        for _ in range(3):
+            nr.render(ro, rd, rd)
+        barrier()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        KN = max(3, min(K, 20))
+        n0.record()
+        for i in range(KN):
+            o_i = dev_batches[i % N_BATCHES][0][:n_nerf]; d_i = dev_batches[i % N_BATCHES][1][:n_nerf]
+            nr.render(o_i, d_i, d_i)
+        n1.record()
+        barrier()
+        nm = torch.tensor([n0.elapsed_time(n1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(nm, op=dist.ReduceOp.MAX)
+        rps = world * n_nerf * KN / (float(nm.item()) * 1e-3)
+        flop_per_ray = (64 + 192) * 593408 * 2
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+                tpeak = float(json.load(fh)['bf16_tflops_sustained'])
+        except Exception:
+            tpeak = 1400.0
+        nerf = {'value': rps, 'unit': 'rays/s', 'workload': 'vanilla NeRF hierarchical 64 coarse + 192 fine evaluations per ray (configs[2]), 32768-ray batches, inference',
+                'ms_per_batch': float(nm.item()) / KN, 'roofline': {'bound': 'tensor', 'achieved': rps * flop_per_ray / 1e12 / world, 'peak': tpeak, 'unit': 'TFLOP/s',
+                                                                     'frac': rps * flop_per_ray / 1e12 / world / tpeak, 'flop_per_ray': flop_per_ray,
+                                                                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a multi-kernel step)'}}
+
     if rank == 0:
         peak, peak_src = peaks()
         f_ms = float(np.mean(field_ms))
@@ -315,6 +352,7 @@ def run_ours(args):
                          'note': 'hash table (24.4 MB fp16) is L2-resident by design; traffic (dram bytes) comes from the ncu capture in profiles/'},
             'cpu_baseline': {'value': cpu_rate, 'unit': 'rays/s', 'cores': cores, 'kind': kind, 'sample': sample},
             'train': train,
+            'nerf': nerf,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -328,6 +366,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-train', dest='no_train', action='store_true', help='skip the training arm')
+    ap.add_argument('--no-nerf', dest='no_nerf', action='store_true', help='skip the vanilla-NeRF arm')
     ap.add_argument('--pipeline', type=int, default=4, help='ray batches in flight (CUDA streams); 1 = strictly sequential steps')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup

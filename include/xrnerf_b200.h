@@ -219,6 +219,9 @@ int xrb_nerf_mlp_forward_v2(const void *weight_image, const float *bias, const v
 size_t xrb_nerf_enc_image_bytes(int64_t n_rows, int input_ch);
 int xrb_nerf_pack_embedded(const float *embedded, int64_t n_rows, int input_ch, int input_ch_dirs, void *enc_image, void *stream);
 int xrb_nerf_posenc_tiles(const float *pts, const float *viewdirs, int64_t n_pts, int samples_per_ray, int multires, int multires_dirs, void *enc_image, void *stream);
+/* same, from rays: sample positions o + d*z (GetPts, xrnerf/datasets/pipelines/create.py:588-597) are formed in registers; z_vals f32[n_rays, S] */
+int xrb_nerf_posenc_tiles_rays(const float *rays_o, const float *rays_d, const float *z_vals, const float *viewdirs, int64_t n_rays, int samples_per_ray, int multires, int multires_dirs,
+                               void *enc_image, void *stream);
 
 /* Mip-NeRF cast_rays + MipNerfEmbedder.forward (networks/utils/mip.py:66-129, embedders/mipnerf_embedder.py:43-99, cone, diag):
  * z_vals f32[N,S+1], radii f32[N] -> embedded f32[N*S, 6*(max_deg_point-min_deg_point) + 3 + 6*(max_deg_view-min_deg_view)];

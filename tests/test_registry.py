@@ -133,3 +133,23 @@ def test_hashnerf_network_train_and_test_steps(scene):
     with torch.no_grad():
         ret = net.forward({'rays_o': data['rays_o'][0], 'rays_d': data['rays_d'][0], 'img_ids': data['img_ids'][0]}, is_test=True)
     assert ret['rgb'].shape == (n, 3) and ret['alpha'].shape == (n, 1)
+
+
+@pytest.mark.gpu
+def test_fused_nerf_renderer_matches_network_forward():
+    """xrnerf_b200.nerf.NerfRenderer (positions + encodings formed inside the kernels, 7 launches) == NerfNetwork.forward(is_test) on the same rays"""
+    from xrnerf_b200 import registry as R
+    from xrnerf_b200.nerf import NerfRenderer
+    torch.manual_seed(0)
+    net = R.build_network(NERF_MODEL).cuda()
+    rng = np.random.default_rng(0)
+    n, s = 700, 64
+    o = (rng.random((n, 3)) * 0.2).astype(np.float32); d = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    vd = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    z = np.broadcast_to(np.linspace(2, 6, s, dtype=np.float32), (n, s)).copy()
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    with torch.no_grad():
+        ref = net.forward(dict(rays_o=t(o), rays_d=t(d), viewdirs=t(vd), z_vals=t(z), pts=t(o[:, None] + d[:, None] * z[..., None])), is_test=True)
+    out = NerfRenderer(net, near=2.0, far=6.0, n_samples=s).render(t(o), t(d), t(vd))
+    assert (out['coarse_rgb'] - ref['coarse_rgb']).abs().max().item() <= 2e-3
+    assert (out['rgb'] - ref['rgb']).abs().max().item() <= 5e-3

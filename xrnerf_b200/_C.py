@@ -68,6 +68,7 @@ _SIGS = {
     'xrb_nerf_enc_image_bytes': (_sz, [_i64, _i]),
     'xrb_nerf_pack_embedded': (_i, [P, _i64, _i, _i, P, P]),
     'xrb_nerf_posenc_tiles': (_i, [P, P, _i64, _i, _i, _i, P, P]),
+    'xrb_nerf_posenc_tiles_rays': (_i, [P, P, P, P, _i64, _i, _i, _i, P, P]),
     'xrb_mip_embed': (_i, [P, P, P, P, P, _i, _i, _i, _i, _i, _i, P, P, P, P]),
     'xrb_mip_resample': (_i, [P, P, P, _i, _i, _f, P, P]),
     'xrb_ngp_render': (_i, [_cfg, P, P, P, P, P, _i, _i, _f, _f, _f, _f, _u64, _i64, C.POINTER(C.c_float), _i, _i, P, P, P, P, P, P]),

@@ -415,8 +415,10 @@ __global__ void __launch_bounds__(256) pack_embedded_tiles_kernel(const float *_
     }
 }
 // BaseEmbedder positional encoding (embedders/base.py:26-52) computed straight into the tile image: pts f32[n,3], viewdirs f32[n/S,3]
+// ray mode (rays_o != NULL): `pts` is z_vals f32[n_rays, S] and the sample position o + d*z is formed in registers (GetPts, create.py:588-597,
+// never materialised: 491 MB per 800x800 image in the reference)
 __global__ void __launch_bounds__(256) posenc_tiles_kernel(const float *__restrict__ pts, const float *__restrict__ viewdirs, int64_t n_rows, int samples_per_ray, int multires,
-                                                           int multires_dirs, uint8_t *__restrict__ image) {
+                                                           int multires_dirs, uint8_t *__restrict__ image, const float *__restrict__ rays_o, const float *__restrict__ rays_d) {
     const int ic = 3 + 6 * multires, icd = 3 + 6 * multires_dirs, aux = (ic + 63) / 64, chunks_per_row = (aux + 1) * 8;
     const int64_t n_tiles = (n_rows + 127) / 128, total = n_tiles * 128 * chunks_per_row;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -426,6 +428,12 @@ __global__ void __launch_bounds__(256) posenc_tiles_kernel(const float *__restri
         const int width = is_dir ? icd : ic, k0 = (is_dir ? 0 : blk * 64) + ch * 8;
         float v[8];
         const float *src = row < n_rows ? (is_dir ? viewdirs + 3 * (row / samples_per_ray) : pts + 3 * row) : nullptr;
+        float p3[3];
+        if (src && !is_dir && rays_o) {
+            const int64_t ray = row / samples_per_ray; const float z = pts[row];
+            p3[0] = rays_o[3 * ray] + rays_d[3 * ray] * z; p3[1] = rays_o[3 * ray + 1] + rays_d[3 * ray + 1] * z; p3[2] = rays_o[3 * ray + 2] + rays_d[3 * ray + 2] * z;
+            src = p3;
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             const int k = k0 + q;
@@ -542,8 +550,20 @@ int xrb_nerf_posenc_tiles(const float *pts, const float *viewdirs, int64_t n_pts
     XRB_REQUIRE(pts && viewdirs && enc_image && ((uintptr_t)enc_image & 15) == 0, "nerf_posenc_tiles: null/misaligned pointer");
     const int aux = (3 + 6 * multires + 63) / 64;
     int64_t total = ((n_pts + 127) / 128) * 128 * (aux + 1) * 8, blocks = (total + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
-    posenc_tiles_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pts, viewdirs, n_pts, samples_per_ray, multires, multires_dirs, (uint8_t *)enc_image);
+    posenc_tiles_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pts, viewdirs, n_pts, samples_per_ray, multires, multires_dirs, (uint8_t *)enc_image, nullptr, nullptr);
     return check_launch("nerf_posenc_tiles");
+}
+
+int xrb_nerf_posenc_tiles_rays(const float *rays_o, const float *rays_d, const float *z_vals, const float *viewdirs, int64_t n_rays, int samples_per_ray, int multires, int multires_dirs,
+                               void *enc_image, void *stream) {
+    XRB_REQUIRE(n_rays >= 0 && samples_per_ray >= 1 && multires >= 0 && multires <= 20 && multires_dirs >= 0 && multires_dirs <= 10, "nerf_posenc_tiles_rays: bad size");
+    if (n_rays == 0) return XRB_OK;
+    XRB_REQUIRE(rays_o && rays_d && z_vals && viewdirs && enc_image && ((uintptr_t)enc_image & 15) == 0, "nerf_posenc_tiles_rays: null/misaligned pointer");
+    const int aux = (3 + 6 * multires + 63) / 64;
+    const int64_t n_pts = n_rays * samples_per_ray;
+    int64_t total = ((n_pts + 127) / 128) * 128 * (aux + 1) * 8, blocks = (total + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
+    posenc_tiles_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(z_vals, viewdirs, n_pts, samples_per_ray, multires, multires_dirs, (uint8_t *)enc_image, rays_o, rays_d);
+    return check_launch("nerf_posenc_tiles_rays");
 }
 
 }  // extern "C"

@@ -42,7 +42,8 @@ def sample_pdf(data, N_samples, is_perturb=False, is_test=False):
     det = is_test or not is_perturb
     u = None if det else torch.rand((n, N_samples), device=z.device)
     z_out = torch.empty((n, s + N_samples), dtype=torch.float32, device=z.device)
-    pts = torch.empty((n, s + N_samples, 3), dtype=torch.float32, device=z.device)
+    want_pts = not ('pts' in data and data['pts'] is None)   # the fused renderer forms positions inside the encoding kernel and asks for no pts
+    pts = torch.empty((n, s + N_samples, 3), dtype=torch.float32, device=z.device) if want_pts else None
     _C.check(_C.lib.xrb_nerf_sample_pdf(_C.ptr(z), _C.ptr(w.detach()), _C.ptr(o), _C.ptr(d), _C.ptr(u), n, s, N_samples, _C.ptr(z_out), _C.ptr(pts), _C.stream()), 'sample_pdf')
     data['pts'], data['z_vals'] = pts, z_out
     return data
