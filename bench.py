@@ -95,6 +95,8 @@ def make_scene(rank, n_batches=N_BATCHES):
 def cpu_reference_rate(sample_rays, reps=1):
     """rays/s of the reference path on the host cores: reference march/composite kernels compiled for CPU (oracle/_ref, all
     cores) + C restatement of the tcnn field (oracle port, OpenMP)."""
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (libgomp reads the variable when it is loaded)
+    os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
     from oracle import oracle as O
     O.build()
     port = O.Port()
@@ -335,7 +337,7 @@ def run_ours(args):
         f_ms = float(np.mean(field_ms))
         s_mean = float(np.mean(samples))
         achieved = s_mean * BYTES_PER_SAMPLE / (f_ms * 1e-3) / 1e9
-        cpu_rate, cores, kind, sample, _ = cpu_reference_rate(4096, reps=2)
+        cpu_rate, cores, kind, sample, _ = cpu_reference_rate(4096, reps=2) if world == 1 else (None, os.cpu_count(), 'reference', 'measured at N=1 only', None)
         line = {
             'metric': METRIC, 'value': world * N_RAYS * K / (total_ms_max * 1e-3), 'unit': 'rays/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': total_ms_max / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
