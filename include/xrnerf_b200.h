@@ -233,6 +233,14 @@ int xrb_mip_embed(const float *z_vals, const float *rays_o, const float *rays_d,
  * -> z_out f32[N,S+1]; u f32[N,S+1] optional (NULL = the deterministic linspace of randomized=False). */
 int xrb_mip_resample(const float *z_vals, const float *weights, const float *u, int n_rays, int n_samples, float resample_padding, float *z_out, void *stream);
 
+/* Ray generation on the device: GetRays (+ Mip radii) + GetViewdirs (xrnerf/datasets/pipelines/create.py:205-245,:437-448)
+ * for convention 0, get_rays_np_hash (xrnerf/datasets/load_data/get_rays.py:35-69) for convention 1. c2w_host: 12 floats on the HOST, row-major [3,4]
+ * camera-to-world. pixel_idx i32[n] (row-major pixel numbers) or NULL for the first n pixels. viewdirs / radii may be NULL. */
+int xrb_nerf_get_rays(const float *c2w_host, int H, int W, float fx, float fy, float cx, float cy, int convention, const int32_t *pixel_idx, int64_t n, float *rays_o, float *rays_d,
+                      float *viewdirs, float *radii, void *stream);
+/* GetZvals (create.py:502-531, near/far constants) and, with u f32[n_rays, S] != NULL, PerturbZvals (augment.py:269-283) */
+int xrb_nerf_zvals(int64_t n_rays, int n_samples, float near_, float far_, int lindisp, const float *u, float *z_vals, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

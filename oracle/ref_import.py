@@ -69,3 +69,22 @@ def load(name):
     """e.g. load('embedders.base') -> the reference module xrnerf/models/embedders/base.py"""
     install()
     return importlib.import_module('xrnerf.models.' + name)
+
+
+def load_pipelines():
+    """the reference's dataset pipeline transforms that generate samples on the hot path (GetRays/GetViewdirs/GetBounds/GetZvals/GetPts,
+    datasets/pipelines/create.py; PerturbZvals, augment.py) and get_rays_np_hash (datasets/load_data/get_rays.py), imported unmodified."""
+    install()
+    import mmcv
+    if 'mmcv.parallel' not in sys.modules:
+        par = types.ModuleType('mmcv.parallel'); par.collate = lambda *a, **k: None
+        sys.modules['mmcv.parallel'] = par; mmcv.parallel = par
+        mmcv.utils.digit_version = lambda v: (0,)
+    sys.modules.setdefault('imageio', types.ModuleType('imageio'))
+    for name in ['xrnerf.datasets', 'xrnerf.datasets.pipelines', 'xrnerf.datasets.load_data', 'xrnerf.datasets.utils']:
+        if name not in sys.modules:
+            m = types.ModuleType(name); m.__path__ = [os.path.join(REF, *name.split('.'))]; sys.modules[name] = m
+    create = importlib.import_module('xrnerf.datasets.pipelines.create')
+    augment = importlib.import_module('xrnerf.datasets.pipelines.augment')
+    get_rays = importlib.import_module('xrnerf.datasets.load_data.get_rays')
+    return create, augment, get_rays

@@ -83,6 +83,29 @@ def main():
                 'mip.grad_rgb': g, 'mip.d_raw': rawm_g.grad})
     d4 = mip.resample_along_rays({'rays_o': rays_o, 'rays_d': rays_d, 'radii': radii, 'z_vals': zm, 'weights': d3['weights'].detach().clone()}, False, 'cone', 0.01)
     out.update({'mip.z_resampled': d4['z_vals'], 'mip.means2': d4['samples'][0], 'mip.covs2': d4['samples'][1]})
+    # --- ray generation: GetRays(+radii) / GetViewdirs / GetBounds / GetZvals / PerturbZvals / GetPts and the NGP get_rays_np_hash
+    create, augment, get_rays = R.load_pipelines()
+    Hh, Ww, foc = 12, 20, 27.5
+    K = np.array([[foc, 0, 0.5 * Ww], [0, foc, 0.5 * Hh], [0, 0, 1]], np.float32)
+    pose = torch.tensor([[0.36, -0.48, 0.8, 1.5], [0.8, 0.6, 0.0, -0.7], [-0.48, 0.64, 0.6, 2.2], [0, 0, 0, 1]], dtype=torch.float32)
+    kw = dict(H=Hh, W=Ww, K=K, near=2.0, far=6.0)
+    res = create.GetRays(include_radius=True, **kw)({'pose': pose})
+    res = create.GetViewdirs(**kw)(res)
+    res = create.GetBounds(**kw)(res)
+    res['rays_o'] = res['rays_o'].reshape(-1, 3); res['rays_d_flat'] = res['rays_d'].reshape(-1, 3)
+    res['near'] = res['near'].reshape(-1, 1); res['far'] = res['far'].reshape(-1, 1)
+    zres = create.GetZvals(N_samples=64, lindisp=False, randomized=False, **kw)(dict(rays_o=res['rays_o'], near=res['near'], far=res['far']))
+    zlin = create.GetZvals(N_samples=33, lindisp=True, randomized=False, **kw)(dict(rays_o=res['rays_o'], near=res['near'], far=res['far']))
+    uz = torch.rand(Hh * Ww, 64)
+    orig = torch.rand
+    torch.rand = lambda *a, **k: uz
+    zper = augment.PerturbZvals()({'z_vals': zres['z_vals'].clone()})
+    torch.rand = orig
+    ptsg = create.GetPts()({'rays_o': res['rays_o'], 'rays_d': res['rays_d_flat'], 'z_vals': zres['z_vals']})
+    ro_h, rd_h = get_rays.get_rays_np_hash(Hh, Ww, K, pose[:3, :4].numpy().T.copy())
+    out.update({'gen.pose': pose, 'gen.K': K, 'gen.rays_o': res['rays_o'], 'gen.rays_d': res['rays_d_flat'], 'gen.viewdirs': res['viewdirs'], 'gen.radii': res['radii'].reshape(-1, 1),
+                'gen.z_lin': zres['z_vals'], 'gen.z_lindisp': zlin['z_vals'], 'gen.u': uz, 'gen.z_perturbed': zper['z_vals'], 'gen.pts': ptsg['pts'],
+                'gen.ngp_rays_o': ro_h.reshape(-1, 3).astype(np.float32), 'gen.ngp_rays_d': rd_h.reshape(-1, 3).astype(np.float32)})
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'nerf_golden.npz'),
                         **{k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()})
     print('wrote nerf_golden.npz with', len(out), 'arrays')

@@ -99,3 +99,31 @@ def test_composite_large_vs_numpy_oracle():
     ref = O.nerf_render(raw, z, d, white_bkgd=True)
     data, ret = NerfRender(white_bkgd=True)({'raw': dev(raw), 'z_vals': dev(z), 'rays_d': dev(d)}, is_test=True)
     assert close(ret['rgb'], ref['rgb'], 5e-5) and close(ret['acc'], ref['acc'], 5e-5) and close(data['weights'], ref['weights'], 5e-5)
+
+
+def test_ray_generation_golden():
+    """xrb_nerf_get_rays / xrb_nerf_zvals vs the reference's GetRays(+radii)/GetViewdirs/GetZvals/PerturbZvals and get_rays_np_hash"""
+    import ctypes as C
+    from xrnerf_b200 import _C
+    H, W, K = 12, 20, G['gen.K']
+    n = H * W
+    pose = np.ascontiguousarray(G['gen.pose'][:3, :4], np.float32)
+    o = torch.empty((n, 3), device='cuda'); d = torch.empty((n, 3), device='cuda'); v = torch.empty((n, 3), device='cuda'); r = torch.empty((n, 1), device='cuda')
+    c2w = (C.c_float * 12)(*pose.reshape(-1).tolist())
+    _C.check(_C.lib.xrb_nerf_get_rays(c2w, H, W, float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]), 0, None, n, _C.ptr(o), _C.ptr(d), _C.ptr(v), _C.ptr(r), _C.stream()))
+    assert close(o, G['gen.rays_o']) and close(d, G['gen.rays_d']) and close(v, G['gen.viewdirs']) and np.allclose(r.cpu().numpy(), G['gen.radii'], rtol=1e-4, atol=1e-7)
+    _C.check(_C.lib.xrb_nerf_get_rays(c2w, H, W, float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]), 1, None, n, _C.ptr(o), _C.ptr(d), None, None, _C.stream()))
+    assert close(o, G['gen.ngp_rays_o']) and close(d, G['gen.ngp_rays_d'])
+    # a pixel subset (SelectRays) gives the same rays
+    idx = torch.tensor([0, 7, 19, 20, 239, 101], dtype=torch.int32, device='cuda')
+    o2 = torch.empty((6, 3), device='cuda'); d2 = torch.empty((6, 3), device='cuda')
+    _C.check(_C.lib.xrb_nerf_get_rays(c2w, H, W, float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2]), 1, _C.ptr(idx), 6, _C.ptr(o2), _C.ptr(d2), None, None, _C.stream()))
+    assert torch.equal(d2, d[idx.long()])
+    z = torch.empty((n, 64), device='cuda')
+    _C.check(_C.lib.xrb_nerf_zvals(n, 64, 2.0, 6.0, 0, None, _C.ptr(z), _C.stream()))
+    assert close(z, G['gen.z_lin'])
+    _C.check(_C.lib.xrb_nerf_zvals(n, 64, 2.0, 6.0, 0, _C.ptr(dev(G['gen.u'])), _C.ptr(z), _C.stream()))
+    assert close(z, G['gen.z_perturbed'])
+    z33 = torch.empty((n, 33), device='cuda')
+    _C.check(_C.lib.xrb_nerf_zvals(n, 33, 2.0, 6.0, 1, None, _C.ptr(z33), _C.stream()))
+    assert close(z33, G['gen.z_lindisp'])

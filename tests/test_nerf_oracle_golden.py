@@ -51,3 +51,13 @@ def test_mip():
         assert close(r[k], G['mip.' + k], 2e-5), k
     z2 = O.resample_along_rays(G['mip.z_vals'], G['mip.weights'])
     assert close(z2, G['mip.z_resampled'], 2e-5)
+
+
+def test_ray_generation():
+    r = O.get_rays(G['gen.pose'], 12, 20, G['gen.K'])
+    assert close(r['rays_o'], G['gen.rays_o']) and close(r['rays_d'], G['gen.rays_d']) and close(r['viewdirs'], G['gen.viewdirs']) and close(r['radii'], G['gen.radii'], 1e-6)
+    ro, rd = O.get_rays_ngp(G['gen.pose'][:3, :4].T, 12, 20, G['gen.K'])
+    assert close(ro, G['gen.ngp_rays_o']) and close(rd, G['gen.ngp_rays_d'])
+    assert close(O.z_vals(240, 64, 2.0, 6.0), G['gen.z_lin']) and close(O.z_vals(240, 33, 2.0, 6.0, lindisp=True), G['gen.z_lindisp'])
+    assert close(O.z_vals(240, 64, 2.0, 6.0, u=G['gen.u']), G['gen.z_perturbed'])
+    assert close(G['gen.rays_o'][:, None] + G['gen.rays_d'][:, None] * G['gen.z_lin'][..., None], G['gen.pts'])

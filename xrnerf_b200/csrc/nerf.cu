@@ -297,6 +297,55 @@ __global__ void __launch_bounds__(PDF_WARPS * 32) mip_resample_kernel(int n_rays
     }
 }
 
+
+// Ray generation: GetRays (+ Mip-NeRF radii) + GetViewdirs (datasets/pipelines/create.py:205-245, :437-448) and the
+// NGP-convention get_rays_np_hash (datasets/load_data/get_rays.py:35-69), one thread per pixel, any pixel subset.
+//   convention 0 (NeRF / Mip): dirs = ((i-cx)/fx, -(j-cy)/fy, -1), rays_d = c2w[:3,:3] dirs, viewdirs = rays_d/|rays_d|,
+//                              radii = |rays_d(j,i) - rays_d(j+1,i)| * 2/sqrt(12) (last row reuses row H-3, create.py:237-243)
+//   convention 1 (NGP):        pixel centres +0.5, dirs = ((i-cx)/fx, (j-cy)/fy, 1), rays_d normalised, pose given as [4,3] (ngp xforms)
+struct RayGenParams { float c2w[12]; float fx, fy, cx, cy; int H, W, convention; };
+__device__ __forceinline__ void raygen_dir(const RayGenParams &p, float i, float j, float d[3]) {
+    float x, y, z;
+    if (p.convention == 0) { x = (i - p.cx) / p.fx; y = -(j - p.cy) / p.fy; z = -1.f; }
+    else { x = (i + 0.5f - p.cx) / p.fx; y = (j + 0.5f - p.cy) / p.fy; z = 1.f; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) d[c] = (x * p.c2w[4 * c] + y * p.c2w[4 * c + 1]) + z * p.c2w[4 * c + 2];
+}
+__global__ void __launch_bounds__(256) get_rays_kernel(RayGenParams p, const int32_t *__restrict__ pixel_idx, int64_t n, float *__restrict__ rays_o, float *__restrict__ rays_d,
+                                                       float *__restrict__ viewdirs, float *__restrict__ radii) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int pix = pixel_idx ? pixel_idx[t] : (int)t;
+        const int j = pix / p.W, i = pix % p.W;
+        float d[3]; raygen_dir(p, (float)i, (float)j, d);
+        const float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        if (p.convention == 1) { d[0] /= nrm; d[1] /= nrm; d[2] /= nrm; }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { rays_o[3 * t + c] = p.c2w[4 * c + 3]; rays_d[3 * t + c] = d[c]; if (viewdirs) viewdirs[3 * t + c] = p.convention == 1 ? d[c] : d[c] / nrm; }
+        if (radii) {
+            const int ja = j < p.H - 1 ? j : p.H - 3;   // dx = cat([dx, dx[-2:-1]]): the last row takes dx of row H-3
+            float a[3], b[3]; raygen_dir(p, (float)i, (float)ja, a); raygen_dir(p, (float)i, (float)(ja + 1), b);
+            const float dx = sqrtf((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
+            radii[t] = dx * 2.f / sqrtf(12.f);
+        }
+    }
+}
+// GetZvals (create.py:502-531, randomized=False) + PerturbZvals (augment.py:269-283) when u != NULL: one thread per (ray, sample)
+__global__ void __launch_bounds__(256) zvals_kernel(int64_t n_rays, int S, float near_, float far_, int lindisp, const float *__restrict__ u, float *__restrict__ z_out) {
+    const float step = 1.0f / (float)(S - 1);
+    auto zat = [&](int k) { float t = k < S / 2 ? step * (float)k : 1.0f - step * (float)(S - 1 - k);   // torch.linspace
+                            return lindisp ? 1.f / (1.f / near_ * (1.f - t) + 1.f / far_ * t) : near_ * (1.f - t) + far_ * t; };
+    const int64_t total = n_rays * S;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % S);
+        float z = zat(k);
+        if (u) {
+            float lower = k == 0 ? z : 0.5f * (z + zat(k - 1)), upper = k == S - 1 ? z : 0.5f * (zat(k + 1) + z);
+            z = lower + (upper - lower) * u[idx];
+        }
+        z_out[idx] = z;
+    }
+}
+
 }  // namespace xrb
 
 using namespace xrb;
@@ -372,6 +421,28 @@ int xrb_mip_resample(const float *z_vals, const float *weights, const float *u, 
     XRB_REQUIRE(z_vals && weights && z_out, "mip_resample: null pointer");
     mip_resample_kernel<<<(n_rays + PDF_WARPS - 1) / PDF_WARPS, PDF_WARPS * 32, 0, (cudaStream_t)stream>>>(n_rays, n_samples, resample_padding, z_vals, weights, u, z_out);
     return check_launch("mip_resample");
+}
+
+int xrb_nerf_get_rays(const float *c2w_host, int H, int W, float fx, float fy, float cx, float cy, int convention, const int32_t *pixel_idx, int64_t n, float *rays_o, float *rays_d,
+                      float *viewdirs, float *radii, void *stream) {
+    XRB_REQUIRE(H >= 1 && W >= 1 && n >= 0 && (convention == 0 || convention == 1), "get_rays: bad arguments");
+    XRB_REQUIRE(!(radii && H < 3), "get_rays: radii need H >= 3");
+    if (n == 0) return XRB_OK;
+    XRB_REQUIRE(c2w_host && rays_o && rays_d, "get_rays: null pointer");
+    RayGenParams p; for (int k = 0; k < 12; ++k) p.c2w[k] = c2w_host[k];
+    p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.H = H; p.W = W; p.convention = convention;
+    int64_t blocks = (n + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
+    get_rays_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, pixel_idx, n, rays_o, rays_d, viewdirs, radii);
+    return check_launch("get_rays");
+}
+
+int xrb_nerf_zvals(int64_t n_rays, int n_samples, float near_, float far_, int lindisp, const float *u, float *z_vals, void *stream) {
+    XRB_REQUIRE(n_rays >= 0 && n_samples >= 2, "zvals: bad size");
+    if (n_rays == 0) return XRB_OK;
+    XRB_REQUIRE(z_vals, "zvals: null pointer");
+    int64_t blocks = (n_rays * n_samples + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
+    zvals_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n_rays, n_samples, near_, far_, lindisp, u, z_vals);
+    return check_launch("zvals");
 }
 
 }  // extern "C"
