@@ -177,6 +177,17 @@ int xrb_ngp_render(const xrb_ngp_config *cfg, const void *table_fp16, const void
                    int dens_act, float *rgb_out, float *alpha_out, int32_t *numsteps, int32_t *counters, void *workspace,
                    void *stream);
 
+/* Single-launch variant: march + hash encode + MLPs (tcgen05) + composite in ONE persistent warp-specialised kernel; no per-sample
+ * buffer exists, so there is no max_samples / overflow case. Same arithmetic as xrb_ngp_render (sample positions bit-identical; the
+ * composite is a segmented warp scan: fp32 re-association only). `workspace`: xrb_ngp_render_fused_workspace() bytes, 256-byte
+ * aligned, ZEROED ONCE by the caller at allocation (the kernel leaves its scheduler words zero on exit); one workspace per stream.
+ * n_samples_out i32[n_rays] (samples per ray) may be NULL. alpha_out f32[n_rays]. */
+size_t xrb_ngp_render_fused_workspace(void);
+int xrb_ngp_render_fused(const xrb_ngp_config *cfg, const void *table_fp16, const void *weight_image, const uint8_t *bitfield,
+                         const float *rays_o, const float *rays_d, int n_rays, float aabb0, float aabb1, float near_distance,
+                         float cone_angle, uint64_t seed, int64_t n_prior_calls, const float *bg3_host, int rgb_act, int dens_act,
+                         float *rgb_out, float *alpha_out, int32_t *n_samples_out, void *workspace, void *stream);
+
 /* measurement hook: cudaEvent_t handles recorded right before / after the field kernel inside xrb_ngp_render (NULL disables) */
 int xrb_ngp_render_set_profile_events(void *before_field, void *after_field);
 

@@ -1,0 +1,55 @@
+"""Developer timing probe: single-launch fused NGP render vs the 5-launch path (sequential and with batches in flight on several streams)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from xrnerf_b200 import synth, _C
+from xrnerf_b200.ngp import NgpField, NgpRenderer
+
+
+def main():
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+    nb = 24
+    grid = synth.lego_like_density_grid(0)
+    bf, _ = synth.bitfield_from_grid_numpy(grid)
+    bf = torch.from_numpy(bf).cuda()
+    f = NgpField().cuda()
+    batches = []
+    for b in range(nb):
+        o, d, _, _ = synth.ray_batch(N, seed=b + 1)
+        batches.append((torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()))
+    r = NgpRenderer(f)
+    rgb_u, alpha_u, ns_u, _ = r.render(*batches[0], bf)
+    r2 = NgpRenderer(f)
+    rgb, alpha, ns = r2.render_fused(*batches[0], bf)
+    torch.cuda.synchronize()
+    print('samples/ray %.2f  ns equal %s  max|drgb| %.2e' % (ns.float().mean().item(), torch.equal(ns, ns_u[:, 0]), (rgb - rgb_u).abs().max().item()), flush=True)
+
+    def run(fn, P, steps=96):
+        streams = [torch.cuda.Stream() for _ in range(P)]
+        rs = [NgpRenderer(f) for _ in range(P)]
+        for w in range(2):
+            for k in range(P):
+                with torch.cuda.stream(streams[k]):
+                    fn(rs[k], *batches[k % nb], bf)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(P):
+            streams[k].wait_event(e0)
+        for i in range(steps):
+            with torch.cuda.stream(streams[i % P]):
+                fn(rs[i % P], *batches[i % nb], bf)
+        for k in range(P):
+            torch.cuda.current_stream().wait_stream(streams[k])
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
+    for P in (1, 2, 4):
+        tu = run(lambda rr, o, d, b: rr.render(o, d, b), P)
+        tf = run(lambda rr, o, d, b: rr.render_fused(o, d, b), P)
+        print(f'P={P}: unfused {tu:.3f} ms ({N / tu / 1e3:.1f} Mrays/s)   fused {tf:.3f} ms ({N / tf / 1e3:.1f} Mrays/s)', flush=True)
+
+
+if __name__ == '__main__':
+    main()

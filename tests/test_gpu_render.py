@@ -69,6 +69,63 @@ def test_render_full_image_properties(scene, setup):
     assert cnt.cpu().numpy()[1] == ns[:, 0].sum()
 
 
+def test_fused_single_launch_matches_oracle_and_unfused(port, scene, setup):
+    """xrb_ngp_render_fused (one launch: march + encode + tcgen05 MLPs + composite) vs the oracle chain and vs the 5-launch path.
+    samples per ray: bit-exact. rgb/alpha: 2e-3 vs the oracle (fp16 field), 2e-5 vs the unfused CUDA path (identical field arithmetic, the
+    composite is a segmented scan instead of a sequential product)."""
+    from xrnerf_b200.ngp import NgpRenderer
+    try:
+        from oracle.oracle import Ref, have_ref
+        ref = Ref(serial=True) if have_ref() else None
+    except Exception:
+        ref = None
+    f, table, dens, color = setup
+    o, d = scene['rays_o'], scene['rays_d']
+    bg = (0.1, 0.5, 0.9)
+    r, r2 = NgpRenderer(f, bg=bg), NgpRenderer(f, bg=bg)
+    for call in range(3):  # calls 1, 2 exercise the advanced host RNG and the kernel's self-resetting scheduler words
+        rgb, alpha, ns = r.render_fused(dev(o), dev(d), dev(scene['bitfield']))
+        rgb_u, alpha_u, ns_u, _ = r2.render(dev(o), dev(d), dev(scene['bitfield']))
+        rgb_ref, alpha_ref, ns_ref, cnt_ref = oracle_render(port, ref, scene, table, dens, color, o, d, bg, n_prior=call)
+        assert np.array_equal(ns.cpu().numpy(), ns_ref[:, 0])
+        assert np.abs(rgb.cpu().numpy() - rgb_ref).max() <= 2e-3 and np.abs(alpha.cpu().numpy() - alpha_ref).max() <= 2e-3
+        assert (rgb - rgb_u).abs().max().item() <= 2e-5 and (alpha - alpha_u).abs().max().item() <= 2e-5
+    assert int(r._ws_fused[:8].view(torch.int32).abs().sum()) == 0   # scheduler words back to zero
+
+
+@pytest.mark.parametrize('n', [1, 31, 33, 1000])
+def test_fused_ragged_sizes(scene, setup, n):
+    from xrnerf_b200.ngp import NgpRenderer
+    f = setup[0]
+    o, d, bf = dev(scene['rays_o'][:n]), dev(scene['rays_d'][:n]), dev(scene['bitfield'])
+    a, b = NgpRenderer(f, bg=(1.0, 1.0, 1.0)), NgpRenderer(f, bg=(1.0, 1.0, 1.0))
+    rgb, alpha, ns = a.render_fused(o, d, bf)
+    rgb_u, alpha_u, ns_u, _ = b.render(o, d, bf)
+    assert torch.equal(ns, ns_u[:, 0]) and (rgb - rgb_u).abs().max().item() <= 2e-5 and (alpha - alpha_u).abs().max().item() <= 2e-5
+
+
+def test_fused_full_image_and_dense_grid(scene, setup):
+    """BASELINE-size image (640 000 rays) through the single-launch kernel == the 5-launch path; and an ALL-ONES occupancy grid (the first
+    256 training iterations' worst case: every ray takes hundreds of samples, several 64-sample march rounds per ray)."""
+    from xrnerf_b200 import synth
+    from xrnerf_b200.ngp import NgpRenderer
+    f = setup[0]
+    o, d = synth.get_rays_ngp(scene['poses'][7])
+    a, b = NgpRenderer(f, bg=(0.25, 0.5, 0.75), samples_per_ray_budget=48), NgpRenderer(f, bg=(0.25, 0.5, 0.75), samples_per_ray_budget=48)
+    rgb, alpha, ns = a.render_fused(dev(o), dev(d), dev(scene['bitfield']))
+    rgb_u, alpha_u, ns_u, _ = b.render(dev(o), dev(d), dev(scene['bitfield']))
+    assert torch.equal(ns, ns_u[:, 0]) and (rgb - rgb_u).abs().max().item() <= 2e-5 and (alpha - alpha_u).abs().max().item() <= 2e-5
+    miss = ns == 0
+    assert miss.any() and (alpha[miss] == 0).all()
+    n = 2048
+    ones = torch.full_like(dev(scene['bitfield']), 255)
+    a2, b2 = NgpRenderer(f, bg=(0.0, 0.0, 0.0)), NgpRenderer(f, bg=(0.0, 0.0, 0.0), samples_per_ray_budget=1024)
+    rgb, alpha, ns = a2.render_fused(dev(o[:n * 300:300]), dev(d[:n * 300:300]), ones)
+    rgb_u, alpha_u, ns_u, _ = b2.render(dev(o[:n * 300:300]), dev(d[:n * 300:300]), ones)
+    assert int(ns.max()) > 128 and torch.equal(ns, ns_u[:, 0])
+    assert (rgb - rgb_u).abs().max().item() <= 1e-4 and (alpha - alpha_u).abs().max().item() <= 1e-4
+
+
 def test_trainer_step_reduces_loss_and_matches_autograd_path(scene, setup):
     """fused training step (xrnerf_b200.train.NgpTrainer) vs the registry/autograd path on the same batch: same loss, and the loss goes down."""
     from xrnerf_b200 import synth

@@ -75,7 +75,16 @@ __device__ __forceinline__ void tc_read_out16(TcWarpgroup &c, float *out) {
     tc::tmem_ld16(taddr, out);
 }
 
-// Density half of the field: returns density_net's 16 fp16-rounded outputs for my sample.
+// Density half of the field, the 32 encoded features already sitting in chunks 0..3 of my A row: density_net's 16 fp16-rounded outputs.
+__device__ __forceinline__ void tc_density_from_a(TcWarpgroup &c, const WeightImageLayout &L, int density_hidden, float *dout) {
+    tc_layer<32, 64>(c, L.d_in);
+    for (int h = 0; h < density_hidden - 1; ++h) { tc_epilogue_relu_to_a(c); tc_layer<64, 64>(c, L.d_hid[h]); }
+    tc_epilogue_relu_to_a(c);
+    tc_layer<64, 16>(c, L.d_out);
+    tc_read_out16(c, dout);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dout[k] = round_h(dout[k]);
+}
 __device__ __forceinline__ void tc_density(TcWarpgroup &c, const WeightImageLayout &L, int density_hidden, const __half2 *__restrict__ table, const HashGridDev &g, float x, float y,
                                            float z, float *dout) {
 #pragma unroll
@@ -85,20 +94,11 @@ __device__ __forceinline__ void tc_density(TcWarpgroup &c, const WeightImageLayo
         for (int k = 0; k < 4; ++k) { float2 f = hash_level(table, g, 4 * q + k, x, y, z); e[k] = pack_h2(f.x, f.y); }
         a_store_chunk(c, q, make_uint4(e[0], e[1], e[2], e[3]));
     }
-    tc_layer<32, 64>(c, L.d_in);
-    for (int h = 0; h < density_hidden - 1; ++h) { tc_epilogue_relu_to_a(c); tc_layer<64, 64>(c, L.d_hid[h]); }
-    tc_epilogue_relu_to_a(c);
-    tc_layer<64, 16>(c, L.d_out);
-    tc_read_out16(c, dout);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) dout[k] = round_h(dout[k]);
+    tc_density_from_a(c, L, density_hidden, dout);
 }
 
-// Whole field (HashNerfMLP.run_mlp, hashnerf_mlp.py:55-79): raw = (rgb[3], density[1]) for my sample
-__device__ __forceinline__ float4 tc_field(TcWarpgroup &c, const WeightImageLayout &L, int density_hidden, int color_hidden, const __half2 *__restrict__ table,
-                                           const HashGridDev &g, float x, float y, float z, float dx, float dy, float dz) {
-    float dout[16];
-    tc_density(c, L, density_hidden, table, g, x, y, z, dout);
+// Colour half (HashNerfMLP.run_mlp, hashnerf_mlp.py:66-79) given density_net's outputs: raw = (rgb[3], density[1]) for my sample
+__device__ __forceinline__ float4 tc_color_from_density(TcWarpgroup &c, const WeightImageLayout &L, int color_hidden, const float *dout, float dx, float dy, float dz) {
     float sh[16];
     sh4(dx, dy, dz, sh);
     // colour-net input row: density_out[1:16] (15) ++ SH (16) ++ 1.0 pad (tcnn.Network pads 31 -> 32 with ones)
@@ -118,6 +118,13 @@ __device__ __forceinline__ float4 tc_field(TcWarpgroup &c, const WeightImageLayo
     float cout[16];
     tc_read_out16(c, cout);
     return make_float4(round_h(cout[0]), round_h(cout[1]), round_h(cout[2]), dout[0]);
+}
+// Whole field: hash encode + both nets
+__device__ __forceinline__ float4 tc_field(TcWarpgroup &c, const WeightImageLayout &L, int density_hidden, int color_hidden, const __half2 *__restrict__ table,
+                                           const HashGridDev &g, float x, float y, float z, float dx, float dy, float dz) {
+    float dout[16];
+    tc_density(c, L, density_hidden, table, g, x, y, z, dout);
+    return tc_color_from_density(c, L, color_hidden, dout, dx, dy, dz);
 }
 
 // ---- CTA-level setup shared by the kernels that use the warpgroup evaluator

@@ -147,3 +147,27 @@ class NgpRenderer:
                                        _C.ptr(numsteps), _C.ptr(counters), _C.ptr(self._ws), _C.stream()), 'ngp_render')
         self.calls += 1
         return rgb, alpha, numsteps, counters
+
+    def render_fused(self, rays_o, rays_d, bitfield, out=None, ws=None):
+        """Single-launch render (xrb_ngp_render_fused). Returns (rgb [n,3], alpha [n,1], n_samples i32[n]). `ws`: a zero-initialised workspace
+        owned by the caller (one per stream when several batches are in flight); default: one per renderer."""
+        _C.require_cuda(rays_o, rays_d, bitfield)
+        f = self.field
+        f.refresh()
+        n = rays_o.shape[0]
+        if ws is None:
+            if getattr(self, '_ws_fused', None) is None or self._ws_fused.device != rays_o.device:
+                self._ws_fused = torch.zeros(_C.lib.xrb_ngp_render_fused_workspace(), dtype=torch.uint8, device=rays_o.device)
+            ws = self._ws_fused
+        if out is None:
+            key = ('fused', n, rays_o.device)
+            if key not in self._out:
+                self._out[key] = (torch.empty((n, 3), dtype=torch.float32, device=rays_o.device), torch.empty((n, 1), dtype=torch.float32, device=rays_o.device),
+                                  torch.empty(n, dtype=torch.int32, device=rays_o.device))
+            out = self._out[key]
+        rgb, alpha, ns = out
+        _C.check(_C.lib.xrb_ngp_render_fused(f.cfg, _C.ptr(f._table16), _C.ptr(f._image), _C.ptr(bitfield), _C.ptr(rays_o), _C.ptr(rays_d), n, self.aabb[0], self.aabb[1],
+                                             self.near, self.cone, 9121, self.calls, _C.float3(self.bg), self.rgb_act, self.dens_act, _C.ptr(rgb), _C.ptr(alpha), _C.ptr(ns),
+                                             _C.ptr(ws), _C.stream()), 'ngp_render_fused')
+        self.calls += 1
+        return rgb, alpha, ns
