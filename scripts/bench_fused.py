@@ -45,8 +45,23 @@ def main():
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / steps
 
-    for P in (1, 2, 4):
-        tu = run(lambda rr, o, d, b: rr.render(o, d, b), P)
+    if int(os.environ.get('XRB_FUSED_DBG', '0')) & 8:
+        torch.cuda.synchronize()
+        tail = r2._ws_fused[-148 * 128:].view(torch.int64).reshape(148, 16).cpu().numpy()
+        t0 = tail[:, 0].min()
+        st, en = (tail[:, 0] - t0) / 1e3, (tail[:, 1] - t0) / 1e3
+        print('CTA start us: min %.1f p50 %.1f max %.1f | end us: min %.1f p50 %.1f max %.1f' % (st.min(), np.median(st), st.max(), en.min(), np.median(en), en.max()))
+        print('late starters (>20us):', int((st > 20).sum()), ' distinct SMs:', len(set(tail[:, 2].tolist())), ' tiles/CTA: mean %.1f max %d' % (tail[:, 3].mean(), tail[:, 3].max()))
+        act = tail[:, 3] > 0
+        mhz = 1.9e3
+        print('field WG us/CTA: poll %.0f waitfull %.0f copy %.0f compute %.0f post %.0f  (tiles %.1f)' % tuple(list(tail[act, 4:9].mean(0) / mhz) + [tail[act, 3].mean()]))
+        print('producers us/CTA (sum over 10 warps): march %.0f setup %.0f gather %.0f mailwait %.0f fold %.0f slotwait %.0f other %.0f' % tuple(tail[act, 9:16].mean(0) / mhz))
+        import collections
+        cnt = collections.Counter(tail[:, 2].tolist())
+        print('CTAs per SM histogram:', collections.Counter(cnt.values()))
+    only_fused = len(sys.argv) > 2
+    for P in (1, 4):
+        tu = 1.0 if only_fused else run(lambda rr, o, d, b: rr.render(o, d, b), P)
         tf = run(lambda rr, o, d, b: rr.render_fused(o, d, b), P)
         print(f'P={P}: unfused {tu:.3f} ms ({N / tu / 1e3:.1f} Mrays/s)   fused {tf:.3f} ms ({N / tf / 1e3:.1f} Mrays/s)', flush=True)
 
