@@ -14,10 +14,11 @@ struct HashGridDev {
     float scale[MAX_LEVELS];
     uint32_t res[MAX_LEVELS];
     int n_levels;
+    uint32_t hashed_mask;             // bit l: level l is hashed (its table is the 2^log2_hashmap_size cap), else dense
 };
 
 inline int64_t hashgrid_build(const xrb_ngp_config *cfg, HashGridDev *g) {
-    g->n_levels = cfg->n_levels;
+    g->n_levels = cfg->n_levels; g->hashed_mask = 0;
     const float log2_pls = log2f(cfg->per_level_scale);
     uint32_t off = 0;
     for (int l = 0; l < cfg->n_levels; ++l) {
@@ -27,6 +28,7 @@ inline int64_t hashgrid_build(const xrb_ngp_config *cfg, HashGridDev *g) {
         uint32_t p = cube > maxp ? maxp : (uint32_t)cube;
         p = (p + 7u) / 8u * 8u;
         uint32_t cap = 1u << cfg->log2_hashmap_size; if (p > cap) p = cap;
+        if (cube > p) g->hashed_mask |= 1u << l;   // then p == cap, a power of two: `% hashmap_size` is a mask
         g->offset[l] = off; g->scale[l] = scale; g->res[l] = res; off += p;
     }
     g->offset[cfg->n_levels] = off;
@@ -55,20 +57,25 @@ __device__ __forceinline__ float round_h(float x) { return __half2float(__float2
 __device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t z, uint32_t hashmap_size, uint32_t res) {
     // tcnn grid.h grid_index(): dense strides while they fit, else the coherent prime hash; then `% hashmap_size`.
     // The modulo is strength-reduced without changing its value (an integer division costs 3 XU-pipe ops on sm_100):
-    //   hashed levels have hashmap_size == 2^log2_hashmap_size (the cap)          -> mask;
+    //   hashed levels have hashmap_size == 2^log2_hashmap_size (the cap)          -> mask (never the generic `%`: it costs ~130 issue slots);
     //   dense levels have index <= res^3 + res^2 + res < 2 * hashmap_size          -> one conditional subtract.
     if ((uint64_t)res * res * res > hashmap_size) {   // uniform per level
         uint32_t h = x ^ (y * 2654435761u) ^ (z * 805459861u);
-        return (hashmap_size & (hashmap_size - 1)) == 0 ? (h & (hashmap_size - 1)) : (h % hashmap_size);
+        return h & (hashmap_size - 1);   // a hashed level's table is always the 2^log2_hashmap_size cap (hashgrid_build)
     }
     uint32_t index = x + y * res + z * res * res;
     return index >= hashmap_size ? index - hashmap_size : index;
 }
 
-// one level of the multiresolution hash encoding: returns the two interpolated features (fp32, NOT yet rounded)
+// one level of the multiresolution hash encoding: returns the two interpolated features (fp32, NOT yet rounded).
+// Index arithmetic is tcnn's grid_index() strength-reduced without changing any value:
+//   hashed level (res^3 > table size == 2^log2_hashmap_size): (x ^ y*P1 ^ z*P2) & (size-1); the two products are shared by the 8 corners
+//   dense level: x + y*res + z*res^2 < 2*size -> one conditional subtract instead of `% size`
+// (the generic `%` compiled to ~130 predicated-off but ISSUED instructions per level: ncu r01d source view)
 __device__ __forceinline__ float2 hash_level(const __half2 *__restrict__ table, const HashGridDev &g, int l, float x, float y, float z) {
-    const uint32_t hs = g.offset[l + 1] - g.offset[l], res = g.res[l];
-    const __half2 *tl = table + g.offset[l];
+    const uint32_t off = g.offset[l], hs = g.offset[l + 1] - off, res = g.res[l];
+    const __half2 *tl = table + off;
+    asm volatile("" : "+l"(tl));   // keep the level base in a register pair: each gather address is then ONE imad.wide (base + idx*4), not a 64-bit add chain
     const float sc = g.scale[l];
     float px = __fmaf_rn(sc, x, 0.5f), py = __fmaf_rn(sc, y, 0.5f), pz = __fmaf_rn(sc, z, 0.5f);
     int ix_, iy_, iz_;
@@ -76,15 +83,28 @@ __device__ __forceinline__ float2 hash_level(const __half2 *__restrict__ table, 
     const uint32_t gx = (uint32_t)ix_, gy = (uint32_t)iy_, gz = (uint32_t)iz_;
     fx = px - fx; fy = py - fy; fz = pz - fz;
     __half2 v[8];
+    if ((g.hashed_mask >> l) & 1u) {   // uniform per level
+        const uint32_t mask = hs - 1u;
+        const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u, hz0 = gz * 805459861u, hz1 = hz0 + 805459861u;
+        const uint32_t a00 = hy0 ^ hz0, a10 = hy1 ^ hz0, a01 = hy0 ^ hz1, a11 = hy1 ^ hz1, gx1 = gx + 1u;
+        v[0] = __ldg(tl + ((gx ^ a00) & mask)); v[1] = __ldg(tl + ((gx1 ^ a00) & mask));
+        v[2] = __ldg(tl + ((gx ^ a10) & mask)); v[3] = __ldg(tl + ((gx1 ^ a10) & mask));
+        v[4] = __ldg(tl + ((gx ^ a01) & mask)); v[5] = __ldg(tl + ((gx1 ^ a01) & mask));
+        v[6] = __ldg(tl + ((gx ^ a11) & mask)); v[7] = __ldg(tl + ((gx1 ^ a11) & mask));
+    } else {
+        const uint32_t sy = res, sz = res * res, b = gx + gy * sy + gz * sz;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {  // all 8 gathers are issued before any is consumed (8 independent loads in flight per level)
-        uint32_t qx = gx + (c & 1), qy = gy + ((c >> 1) & 1), qz = gz + ((c >> 2) & 1);
-        v[c] = __ldg(tl + grid_index(qx, qy, qz, hs, res));
+        for (int c = 0; c < 8; ++c) {  // all 8 gathers are issued before any is consumed (8 independent loads in flight per level)
+            uint32_t idx = b + (c & 1) + ((c >> 1) & 1) * sy + ((c >> 2) & 1) * sz;
+            idx = idx >= hs ? idx - hs : idx;
+            v[c] = __ldg(tl + idx);
+        }
     }
+    const float ux = 1.f - fx, uy = 1.f - fy, uz = 1.f - fz;
     float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        float w = ((c & 1) ? fx : 1.f - fx) * ((c & 2) ? fy : 1.f - fy) * ((c & 4) ? fz : 1.f - fz);
+        float w = ((c & 1) ? fx : ux) * ((c & 2) ? fy : uy) * ((c & 4) ? fz : uz);
         float2 f = __half22float2(v[c]);
         acc.x += w * f.x; acc.y += w * f.y;
     }

@@ -336,7 +336,8 @@ __global__ void __launch_bounds__((4 * FR_N_WG + N_PROD) * 32, FR_CTAS_PER_SM) n
     }
 }
 
-constexpr int FUSED_N_PROD = 16, FUSED_N_SLOTS = 5;
+constexpr int FUSED_MAX_PROD = 24, FUSED_N_SLOTS = 5;
+static int fused_n_prod() { static int v = -1; if (v < 0) { const char *e = getenv("XRB_FUSED_NPROD"); v = e ? atoi(e) : 16; if (v != 16 && v != 20 && v != 24) v = 16; } return v; }
 
 }  // namespace xrb
 
@@ -346,7 +347,7 @@ extern "C" {
 
 size_t xrb_ngp_render_fused_workspace(void) {
     int dev = 0, sms = NUM_SMS; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); sms = NUM_SMS; }
-    return 256 + (size_t)sms * FR_CTAS_PER_SM * FUSED_N_PROD * 32 * FR_TCAP * sizeof(float) + (size_t)sms * FR_CTAS_PER_SM * 128;
+    return 256 + (size_t)sms * FR_CTAS_PER_SM * FUSED_MAX_PROD * 32 * FR_TCAP * sizeof(float) + (size_t)sms * FR_CTAS_PER_SM * 128;
 }
 
 int xrb_ngp_render_fused(const xrb_ngp_config *cfg, const void *table_fp16, const void *weight_image, const uint8_t *bitfield, const float *rays_o, const float *rays_d, int n_rays,
@@ -368,23 +369,27 @@ int xrb_ngp_render_fused(const xrb_ngp_config *cfg, const void *table_fp16, cons
     { static const int dbg = getenv("XRB_FUSED_DBG") ? atoi(getenv("XRB_FUSED_DBG")) : 0; P.dbg = dbg; }
     int dev = 0, sms = NUM_SMS; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     P.sched = (uint32_t *)workspace; P.tscratch = (float *)((uint8_t *)workspace + 256);
-    P.dbg_out = (unsigned long long *)((uint8_t *)workspace + 256 + (size_t)sms * FR_CTAS_PER_SM * FUSED_N_PROD * 32 * FR_TCAP * sizeof(float));
-    auto k = ngp_render_fused_kernel<FUSED_N_PROD, FUSED_N_SLOTS>;
-    const size_t smem = fused_smem_bytes<FUSED_N_PROD, FUSED_N_SLOTS>(P.image_bytes);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (getenv("XRB_FUSED_CARVEOUT")) cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("XRB_FUSED_CARVEOUT")));
-        if (getenv("XRB_DEBUG")) {
-            int per_sm = -1; cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, (4 * FR_N_WG + FUSED_N_PROD) * 32, smem);
-            cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k);
-            fprintf(stderr, "[xrb] fused: occupancy err=%d per_sm=%d smem=%zu regs=%d static_smem=%zu local=%zu\n", (int)oe, per_sm, smem, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes);
-        }
-        attr_set = true;
-    }
+    P.dbg_out = (unsigned long long *)((uint8_t *)workspace + 256 + (size_t)sms * FR_CTAS_PER_SM * FUSED_MAX_PROD * 32 * FR_TCAP * sizeof(float));
     const int64_t n_groups = ((int64_t)n_rays + 31) / 32;
     int grid = sms * FR_CTAS_PER_SM; if (n_groups < grid) grid = (int)n_groups;
-    k<<<grid, (4 * FR_N_WG + FUSED_N_PROD) * 32, smem, (cudaStream_t)stream>>>(P);
+    const int np = fused_n_prod();
+#define XRB_LAUNCH_FUSED(NP)                                                                                                                           \
+    do {                                                                                                                                               \
+        auto k = ngp_render_fused_kernel<NP, FUSED_N_SLOTS>;                                                                                           \
+        const size_t smem = fused_smem_bytes<NP, FUSED_N_SLOTS>(P.image_bytes);                                                                        \
+        static bool attr_set = false;                                                                                                                  \
+        if (!attr_set) {                                                                                                                               \
+            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                                           \
+            if (getenv("XRB_DEBUG")) {                                                                                                                 \
+                cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k);                                                                                  \
+                fprintf(stderr, "[xrb] fused<%d>: smem=%zu regs=%d local=%zu\n", NP, smem, fa.numRegs, fa.localSizeBytes);                             \
+            }                                                                                                                                          \
+            attr_set = true;                                                                                                                           \
+        }                                                                                                                                              \
+        k<<<grid, (4 * FR_N_WG + NP) * 32, smem, (cudaStream_t)stream>>>(P);                                                                           \
+    } while (0)
+    if (np == 24) XRB_LAUNCH_FUSED(24); else if (np == 20) XRB_LAUNCH_FUSED(20); else XRB_LAUNCH_FUSED(16);
+#undef XRB_LAUNCH_FUSED
     return check_launch("ngp_render_fused");
 }
 

@@ -52,7 +52,13 @@ __device__ __forceinline__ void tc_layer(TcWarpgroup &c, uint32_t w_off) {
     tc::tc_fence_after_sync();
 }
 
-// accumulator (64 fp32 columns of my lane) -> ReLU -> fp16 -> my A row (8 chunks)
+// accumulator (64 fp32 columns of my lane) -> fp16 -> ReLU -> my A row (8 chunks). Rounding to fp16 first and clamping the packed pair
+// (one cvt.rn.f16x2 + one max.f16x2 per two values) gives the same bits as clamp-then-round: rounding is monotone and maps 0 to 0.
+__device__ __forceinline__ uint32_t pack_relu_h2(uint32_t a_bits, uint32_t b_bits) {
+    __half2 h = __floats2half2_rn(__uint_as_float(a_bits), __uint_as_float(b_bits));
+    h = __hmax2(h, __float2half2_rn(0.f));
+    return *reinterpret_cast<uint32_t *>(&h);
+}
 __device__ __forceinline__ void tc_epilogue_relu_to_a(TcWarpgroup &c) {
     const uint32_t taddr = c.tmem + (((c.row >> 5) * 32u) << 16);
 #pragma unroll
@@ -62,10 +68,10 @@ __device__ __forceinline__ void tc_epilogue_relu_to_a(TcWarpgroup &c) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             uint4 v;
-            v.x = pack_h2(fmaxf(__uint_as_float(r[8 * q + 0]), 0.f), fmaxf(__uint_as_float(r[8 * q + 1]), 0.f));
-            v.y = pack_h2(fmaxf(__uint_as_float(r[8 * q + 2]), 0.f), fmaxf(__uint_as_float(r[8 * q + 3]), 0.f));
-            v.z = pack_h2(fmaxf(__uint_as_float(r[8 * q + 4]), 0.f), fmaxf(__uint_as_float(r[8 * q + 5]), 0.f));
-            v.w = pack_h2(fmaxf(__uint_as_float(r[8 * q + 6]), 0.f), fmaxf(__uint_as_float(r[8 * q + 7]), 0.f));
+            v.x = pack_relu_h2(r[8 * q + 0], r[8 * q + 1]);
+            v.y = pack_relu_h2(r[8 * q + 2], r[8 * q + 3]);
+            v.z = pack_relu_h2(r[8 * q + 4], r[8 * q + 5]);
+            v.w = pack_relu_h2(r[8 * q + 6], r[8 * q + 7]);
             a_store_chunk(c, half * 4 + q, v);
         }
     }
