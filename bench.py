@@ -233,6 +233,48 @@ def run_ours(args):
     total_ms_max = float(t.item())
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- single-launch arm: the same K steps through xrb_ngp_render_fused (march + encode + tcgen05 MLPs + composite in ONE kernel per batch)
+    evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    fork()
+    for i in range(W):
+        with torch.cuda.stream(streams[i % P]):
+            renderers[i % P].render_fused(*dev_batches[i % N_BATCHES], bf)
+    join()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(main)
+    fork()
+    ns_log = []
+    kev = not os.environ.get('XRB_BENCH_NO_KEVENTS')
+    th0 = time.perf_counter()
+    for i in range(K):
+        st = streams[i % P]
+        with torch.cuda.stream(st):
+            if kev:
+                evk[i][0].record(st)
+            outf = renderers[i % P].render_fused(*dev_batches[(W + i) % N_BATCHES], bf)
+            if kev:
+                evk[i][1].record(st)
+            if i < P:
+                ns_log.append(outf[2])   # per-ray sample counts of this batch; reduced AFTER the timed region (a first-use torch reduction costs ~20 ms of lazy module loading)
+    th1 = time.perf_counter()
+    join()
+    f1.record(main)
+    barrier()
+    if os.environ.get('XRB_BENCH_DEBUG') and kev:
+        gaps = [evk[i][1].elapsed_time(evk[i + 1][0]) for i in range(K - 1)] if P == 1 else []
+        kms = [a.elapsed_time(b) for a, b in evk]
+        print('[bench] kernel ms: first 8', [round(x, 3) for x in kms[:8]], 'p50', round(float(np.median(kms)), 3), '| gaps ms first 8', [round(x, 3) for x in gaps[:8]], 'p50', round(float(np.median(gaps)), 3) if gaps else None, 'max', round(max(gaps), 3) if gaps else None, file=sys.stderr, flush=True)
+    if os.environ.get('XRB_BENCH_DEBUG'):
+        print(f'[bench] fused arm: host issue {1e3 * (th1 - th0) / K:.3f} ms/step, total wall {1e3 * (time.perf_counter() - th0) / K:.3f} ms/step', file=sys.stderr, flush=True)
+    fused_total = torch.tensor([float(f0.elapsed_time(f1))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(fused_total, op=dist.ReduceOp.MAX)
+    fused_total_ms = float(fused_total.item())
+    fused_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evk])) if kev else fused_total_ms / K
+    fused_samples = float(np.mean([float(x.sum().item()) for x in ns_log]))
+    use_fused = args.path == 'fused' or (args.path == 'auto' and fused_total_ms < total_ms_max)
+
     # ---- end-to-end arm: host (pinned) rays in, rgb+alpha out, every step, through the public API; P batches in flight
     slots = [dict(rgb_h=torch.empty((N_RAYS, 3), dtype=torch.float32).pin_memory(), alpha_h=torch.empty((N_RAYS, 1), dtype=torch.float32).pin_memory(),
                   o_d=torch.empty((N_RAYS, 3), dtype=torch.float32, device=dev), d_d=torch.empty((N_RAYS, 3), dtype=torch.float32, device=dev), done=None) for _ in range(P)]
@@ -244,7 +286,7 @@ def run_ours(args):
         o_h, d_h = host_batches[i % len(host_batches)]
         with torch.cuda.stream(st):
             sl['o_d'].copy_(o_h, non_blocking=True); sl['d_d'].copy_(d_h, non_blocking=True)
-            rgb, alpha, _, _ = renderers[i % P].render(sl['o_d'], sl['d_d'], bf)
+            rgb, alpha = (renderers[i % P].render_fused if use_fused else renderers[i % P].render)(sl['o_d'], sl['d_d'], bf)[:2]
             sl['rgb_h'].copy_(rgb, non_blocking=True); sl['alpha_h'].copy_(alpha, non_blocking=True)
             sl['done'] = torch.cuda.Event(); sl['done'].record(st)
 
@@ -338,20 +380,31 @@ def run_ours(args):
         s_mean = float(np.mean(samples))
         achieved = s_mean * BYTES_PER_SAMPLE / (f_ms * 1e-3) / 1e9
         cpu_rate, cores, kind, sample, _ = cpu_reference_rate(4096, reps=2) if world == 1 else (None, os.cpu_count(), 'reference', 'measured at N=1 only', None)
+        chain = {'value': world * N_RAYS * K / (total_ms_max * 1e-3), 'unit': 'rays/s', 'ms_per_step': total_ms_max / K, 'gpu_launches_per_step': 5,
+                 'what': '5 launches per batch on one stream (march count / scan / emit, field, composite), P batches in flight on P streams',
+                 'roofline': {'kernel': 'xrb::ngp_field_tc_kernel<false>', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                              'kernel_ms': f_ms, 'kernel_share_of_step': f_ms / (total_ms_max / K), 'algorithmic_bytes_per_launch': s_mean * BYTES_PER_SAMPLE}}
+        f_bytes = fused_samples * 512 + N_RAYS * 44   # no coords[S,7] / raw[S,4] round trip: gather bytes + 44 B of ray I/O
+        f_ach = f_bytes / (fused_kernel_ms * 1e-3) / 1e9
+        fused = {'value': world * N_RAYS * K / (fused_total_ms * 1e-3), 'unit': 'rays/s', 'ms_per_step': fused_total_ms / K, 'gpu_launches_per_step': 1,
+                 'what': 'ONE launch per batch (xrb_ngp_render_fused: warp-specialised march + hash encode + tcgen05 MLPs + segmented-scan composite), P batches in flight on P streams',
+                 'roofline': {'kernel': 'xrb::ngp_render_fused_kernel', 'bound': 'hbm', 'achieved': f_ach, 'peak': peak, 'unit': 'GB/s', 'frac': f_ach / peak,
+                              'kernel_ms': fused_kernel_ms, 'kernel_share_of_step': 1.0, 'algorithmic_bytes_per_launch': f_bytes}}
+        head = fused if use_fused else chain
         line = {
-            'metric': METRIC, 'value': world * N_RAYS * K / (total_ms_max * 1e-3), 'unit': 'rays/s', 'n_gpus': world, 'steps': K, 'warmup': W,
-            'ms_per_step': total_ms_max / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
+            'metric': METRIC, 'value': head['value'], 'unit': 'rays/s', 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': head['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'rays_per_step_per_gpu': N_RAYS, 'samples_per_ray_mean': s_mean / N_RAYS, 'parallelism': f'ray-sharded x{world}, no data-path collective',
                        'l2': f'inputs larger than L2: {N_BATCHES} distinct ray batches = {N_BATCHES * N_RAYS * 24 / 1e6:.0f} MB cycled (L2 126 MB); the 24.4 MB fp16 hash table stays L2-resident as in production',
-                       'timing': 'one CUDA-event pair around the K steps on the launching stream, max over ranks', 'batches_in_flight': P},
+                       'timing': 'one CUDA-event pair around the K steps on the launching stream, max over ranks', 'batches_in_flight': P,
+                       'path': 'fused single launch' if use_fused else 'chain of 5 launches', 'path_selection': args.path},
             'clocks': clk,
             'e2e': {'value': world * N_RAYS * K / (e2e_ms * 1e-3), 'unit': 'rays/s', 'h2d_bytes_per_step': N_RAYS * 24, 'd2h_bytes_per_step': N_RAYS * 16,
                     'ms_per_step': e2e_ms / K, 'host_wall_ms_per_step': e2e_wall_ms / K},
-            'gpu_launches': 5 * K,
-            'roofline': {'kernel': 'xrb::ngp_field_tc_kernel<false>', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-                         'peak_source': peak_src, 'kernel_ms': f_ms, 'kernel_share_of_step': f_ms / (total_ms_max / K),
-                         'algorithmic_bytes_per_launch': s_mean * BYTES_PER_SAMPLE,
-                         'note': 'hash table (24.4 MB fp16) is L2-resident by design; traffic (dram bytes) comes from the ncu capture in profiles/'},
+            'gpu_launches': head['gpu_launches_per_step'] * K,
+            'roofline': dict(head['roofline'], traffic=None, peak_source=peak_src,
+                             note='hash table (24.4 MB fp16) is L2-resident by design: the gather is served by L1/L2, so DRAM traffic (ncu, profiles/) is far below the algorithmic bytes'),
+            'paths': {'chain': chain, 'fused': fused},
             'cpu_baseline': {'value': cpu_rate, 'unit': 'rays/s', 'cores': cores, 'kind': kind, 'sample': sample},
             'train': train,
             'nerf': nerf,
@@ -369,6 +422,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-train', dest='no_train', action='store_true', help='skip the training arm')
     ap.add_argument('--no-nerf', dest='no_nerf', action='store_true', help='skip the vanilla-NeRF arm')
+    ap.add_argument('--path', default='auto', choices=['auto', 'chain', 'fused'], help='inference path of the headline/e2e numbers: 5-launch chain, single-launch fused kernel, or the faster of the two (both are always measured)')
     ap.add_argument('--pipeline', type=int, default=4, help='ray batches in flight (CUDA streams); 1 = strictly sequential steps')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup

@@ -31,8 +31,7 @@ namespace xrb {
 constexpr uint32_t FR_ROW_BYTES = 80;                    // tile-slot row: 64 B = 32 fp16 features, 16 B = warped direction (3 floats) + pad
 constexpr uint32_t FR_SLOT_BYTES = 128 * FR_ROW_BYTES;   // 80-byte row stride is bank-conflict-free for 16-byte accesses
 constexpr uint32_t FR_TCAP = 64;                         // samples per ray per march round
-constexpr int FR_CTAS_PER_SM = 1;
-constexpr int FR_N_WG = 2;                               // field warpgroups per CTA
+constexpr int FR_MAX_WG = 2;                             // field warpgroups per CTA: 2 (one 768-thread CTA per SM) or 1 (two 384-thread CTAs per SM)
 
 struct FusedParams {
     HashGridDev g;
@@ -47,7 +46,7 @@ struct FusedParams {
     int dbg;             // developer ablation bits (XRB_FUSED_DBG): 1 skip the hash gather, 2 skip the MLP layers, 4 fake march (11 samples/ray)
 };
 
-template <int N_PROD, int N_SLOTS>
+template <int FR_N_WG, int N_PROD, int N_SLOTS>
 struct FusedCtl {
     uint64_t full[N_SLOTS];         // count 4: one arrival per chunk (producer lane 0, or the closing field thread for a skipped quarter)
     uint64_t mail[N_PROD][2];       // count 32: the 32 field threads holding a producer's rows; a producer's chunk k uses mailbox k & 1
@@ -57,19 +56,19 @@ struct FusedCtl {
     uint32_t issued_bcast[FR_N_WG];
     uint32_t tmem_slot, ticket, closed, done, prod_done;
 };
-template <int N_PROD, int N_SLOTS>
+template <int FR_N_WG, int N_PROD, int N_SLOTS>
 __host__ __device__ inline size_t fused_smem_bytes(uint32_t image_bytes) {
-    return 1024 + image_bytes + (size_t)FR_N_WG * 16384 + (size_t)N_SLOTS * FR_SLOT_BYTES + (size_t)N_PROD * 1024 + sizeof(FusedCtl<N_PROD, N_SLOTS>) + 64;
+    return 1024 + image_bytes + (size_t)FR_N_WG * 16384 + (size_t)N_SLOTS * FR_SLOT_BYTES + (size_t)N_PROD * 1024 + sizeof(FusedCtl<FR_N_WG, N_PROD, N_SLOTS>) + 64;
 }
 
 __device__ __forceinline__ void spin_until_ge(volatile uint32_t *p, uint32_t v) {
     while (*p < v) __nanosleep(20);
 }
 
-template <int N_PROD, int N_SLOTS>
-__global__ void __launch_bounds__((4 * FR_N_WG + N_PROD) * 32, FR_CTAS_PER_SM) ngp_render_fused_kernel(const __grid_constant__ FusedParams P) {
+template <int FR_N_WG, int N_PROD, int N_SLOTS>
+__global__ void __launch_bounds__((4 * FR_N_WG + N_PROD) * 32, 3 - FR_N_WG) ngp_render_fused_kernel(const __grid_constant__ FusedParams P) {
     extern __shared__ uint8_t dyn_smem[];
-    using Ctl = FusedCtl<N_PROD, N_SLOTS>;
+    using Ctl = FusedCtl<FR_N_WG, N_PROD, N_SLOTS>;
     uint8_t *base = (uint8_t *)(((uintptr_t)dyn_smem + 1023) & ~(uintptr_t)1023);
     uint8_t *W = base, *A = W + P.image_bytes, *slots = A + (size_t)FR_N_WG * 16384, *mailbox = slots + (size_t)N_SLOTS * FR_SLOT_BYTES;
     Ctl *ctl = (Ctl *)(mailbox + (size_t)N_PROD * 1024);
@@ -281,7 +280,8 @@ __global__ void __launch_bounds__((4 * FR_N_WG + N_PROD) * 32, FR_CTAS_PER_SM) n
                     // ---- results of the previous chunk (its tile ran on the tensor core during this gather): composite
                     if (pending) {
                         const uint32_t kprev = n_submitted - 1;
-                        tc::mbar_wait(&ctl->mail[pw][kprev & 1], (kprev >> 1) & 1);
+                        if (lane == 0) tc::mbar_wait(&ctl->mail[pw][kprev & 1], (kprev >> 1) & 1);   // one lane polls: 32 lanes leaving a spin loop at different
+                        __syncwarp();                                                               // iterations run the scan below diverged (shfl slow path)
                         PTICK(3);
                         const float4 raw = *reinterpret_cast<const float4 *>(mailbox + (size_t)((pw << 1) | (kprev & 1)) * 512 + lane * 16);
                         float alpha = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
@@ -336,8 +336,10 @@ __global__ void __launch_bounds__((4 * FR_N_WG + N_PROD) * 32, FR_CTAS_PER_SM) n
     }
 }
 
-constexpr int FUSED_MAX_PROD = 24, FUSED_N_SLOTS = 5;
-static int fused_n_prod() { static int v = -1; if (v < 0) { const char *e = getenv("XRB_FUSED_NPROD"); v = e ? atoi(e) : 16; if (v != 16 && v != 20 && v != 24) v = 16; } return v; }
+constexpr int FUSED_MAX_PROD_PER_SM = 24;
+// variant 0: one CTA per SM = 2 field warpgroups + 16 producers, 5 tile slots; variant 1: two CTAs per SM, each 1 field warpgroup + 8 producers,
+// 3 tile slots (batches on different streams then share every SM: the tail of one render overlaps the head of the next)
+static int fused_variant() { static int v = -1; if (v < 0) { const char *e = getenv("XRB_FUSED_VARIANT"); v = e ? atoi(e) : 0; if (v != 0 && v != 1) v = 0; } return v; }
 
 }  // namespace xrb
 
@@ -347,7 +349,7 @@ extern "C" {
 
 size_t xrb_ngp_render_fused_workspace(void) {
     int dev = 0, sms = NUM_SMS; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) { cudaGetLastError(); sms = NUM_SMS; }
-    return 256 + (size_t)sms * FR_CTAS_PER_SM * FUSED_MAX_PROD * 32 * FR_TCAP * sizeof(float) + (size_t)sms * FR_CTAS_PER_SM * 128;
+    return 256 + (size_t)sms * FUSED_MAX_PROD_PER_SM * 32 * FR_TCAP * sizeof(float) + (size_t)sms * 2 * 128;
 }
 
 int xrb_ngp_render_fused(const xrb_ngp_config *cfg, const void *table_fp16, const void *weight_image, const uint8_t *bitfield, const float *rays_o, const float *rays_d, int n_rays,
@@ -369,26 +371,25 @@ int xrb_ngp_render_fused(const xrb_ngp_config *cfg, const void *table_fp16, cons
     { static const int dbg = getenv("XRB_FUSED_DBG") ? atoi(getenv("XRB_FUSED_DBG")) : 0; P.dbg = dbg; }
     int dev = 0, sms = NUM_SMS; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     P.sched = (uint32_t *)workspace; P.tscratch = (float *)((uint8_t *)workspace + 256);
-    P.dbg_out = (unsigned long long *)((uint8_t *)workspace + 256 + (size_t)sms * FR_CTAS_PER_SM * FUSED_MAX_PROD * 32 * FR_TCAP * sizeof(float));
+    P.dbg_out = (unsigned long long *)((uint8_t *)workspace + 256 + (size_t)sms * FUSED_MAX_PROD_PER_SM * 32 * FR_TCAP * sizeof(float));
     const int64_t n_groups = ((int64_t)n_rays + 31) / 32;
-    int grid = sms * FR_CTAS_PER_SM; if (n_groups < grid) grid = (int)n_groups;
-    const int np = fused_n_prod();
-#define XRB_LAUNCH_FUSED(NP)                                                                                                                           \
+#define XRB_LAUNCH_FUSED(NWG, NP, NS)                                                                                                                  \
     do {                                                                                                                                               \
-        auto k = ngp_render_fused_kernel<NP, FUSED_N_SLOTS>;                                                                                           \
-        const size_t smem = fused_smem_bytes<NP, FUSED_N_SLOTS>(P.image_bytes);                                                                        \
+        auto k = ngp_render_fused_kernel<NWG, NP, NS>;                                                                                                 \
+        const size_t smem = fused_smem_bytes<NWG, NP, NS>(P.image_bytes);                                                                              \
         static bool attr_set = false;                                                                                                                  \
         if (!attr_set) {                                                                                                                               \
             cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                                           \
             if (getenv("XRB_DEBUG")) {                                                                                                                 \
                 cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k);                                                                                  \
-                fprintf(stderr, "[xrb] fused<%d>: smem=%zu regs=%d local=%zu\n", NP, smem, fa.numRegs, fa.localSizeBytes);                             \
+                fprintf(stderr, "[xrb] fused<%d,%d,%d>: smem=%zu regs=%d local=%zu\n", NWG, NP, NS, smem, fa.numRegs, fa.localSizeBytes);              \
             }                                                                                                                                          \
             attr_set = true;                                                                                                                           \
         }                                                                                                                                              \
-        k<<<grid, (4 * FR_N_WG + NP) * 32, smem, (cudaStream_t)stream>>>(P);                                                                           \
+        int grid = sms * (3 - NWG); if (n_groups < grid) grid = (int)n_groups;                                                                         \
+        k<<<grid, (4 * NWG + NP) * 32, smem, (cudaStream_t)stream>>>(P);                                                                               \
     } while (0)
-    if (np == 24) XRB_LAUNCH_FUSED(24); else if (np == 20) XRB_LAUNCH_FUSED(20); else XRB_LAUNCH_FUSED(16);
+    if (fused_variant() == 1) XRB_LAUNCH_FUSED(1, 8, 3); else XRB_LAUNCH_FUSED(2, 16, 5);
 #undef XRB_LAUNCH_FUSED
     return check_launch("ngp_render_fused");
 }
