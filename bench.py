@@ -374,6 +374,45 @@ def run_ours(args):
                                                                      'frac': rps * flop_per_ray / 1e12 / world / tpeak, 'flop_per_ray': flop_per_ray,
                                                                      'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a multi-kernel step)'}}
 
+    # ---- Mip-NeRF arm (BASELINE configs[3]: 2 levels x 128 cone samples, IPE): the same tcgen05 NerfMLP on IPE tile images, device-resident rays
+    mip = None
+    if not args.no_mip:
+        from xrnerf_b200 import registry as R
+        from xrnerf_b200.nerf import MipNerfRenderer
+        mnet = R.build_network(dict(type='MipNerfNetwork', cfg=dict(phase='test', ray_shape='cone', resample_padding=0.01, use_multiscale=False, coarse_loss_mult=0.1, num_levels=2,
+                                                                    chunk=1024 * 32, bs_data='rays_o'),
+                                    mlp=dict(type='NerfMLP', skips=[4], netdepth=8, netwidth=256, netchunk=1024 * 32, use_viewdirs=True,
+                                             embedder=dict(type='MipNerfEmbedder', min_deg_point=0, max_deg_point=16, min_deg_view=0, max_deg_view=4, use_viewdirs=True, append_identity=True)),
+                                    render=dict(type='MipNerfRender', white_bkgd=True, raw_noise_std=0, rgb_padding=0.001, density_bias=-1, density_activation='softplus'))).to(dev)
+        mr = MipNerfRenderer(mnet, near=2.0, far=6.0, n_samples=128)
+        n_mip = 32768
+        radii = torch.full((n_mip,), 2.0 / (1111.111 * 12 ** 0.5), device=dev)        # GetRays radii of an 800x800 f=1111 camera: |dx| * 2/sqrt(12) (create.py:237-243)
+        for i in range(3):
+            mr.render(dev_batches[0][0][:n_mip], dev_batches[0][1][:n_mip], dev_batches[0][1][:n_mip], radii)
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        KM = max(3, min(K, 20))
+        m0.record()
+        for i in range(KM):
+            o_i = dev_batches[i % N_BATCHES][0][:n_mip]; d_i = dev_batches[i % N_BATCHES][1][:n_mip]
+            mr.render(o_i, d_i, d_i, radii)
+        m1.record()
+        barrier()
+        mm = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(mm, op=dist.ReduceOp.MAX)
+        mrps = world * n_mip * KM / (float(mm.item()) * 1e-3)
+        mflop = 256 * 610304 * 2
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+                tpeak = float(json.load(fh)['bf16_tflops_sustained'])
+        except Exception:
+            tpeak = 1400.0
+        mip = {'value': mrps, 'unit': 'rays/s', 'workload': 'Mip-NeRF 2 levels x 128 conical-frustum samples per ray, IPE 96 + 27 (configs[3]), 32768-ray batches, inference',
+               'ms_per_batch': float(mm.item()) / KM, 'roofline': {'bound': 'tensor', 'achieved': mrps * mflop / 1e12 / world, 'peak': tpeak, 'unit': 'TFLOP/s',
+                                                                   'frac': mrps * mflop / 1e12 / world / tpeak, 'flop_per_ray': mflop,
+                                                                   'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a multi-kernel step)'}}
+
     if rank == 0:
         peak, peak_src = peaks()
         f_ms = float(np.mean(field_ms))
@@ -408,6 +447,7 @@ def run_ours(args):
             'cpu_baseline': {'value': cpu_rate, 'unit': 'rays/s', 'cores': cores, 'kind': kind, 'sample': sample},
             'train': train,
             'nerf': nerf,
+            'mip': mip,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -422,6 +462,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-train', dest='no_train', action='store_true', help='skip the training arm')
     ap.add_argument('--no-nerf', dest='no_nerf', action='store_true', help='skip the vanilla-NeRF arm')
+    ap.add_argument('--no-mip', dest='no_mip', action='store_true', help='skip the Mip-NeRF arm')
     ap.add_argument('--path', default='auto', choices=['auto', 'chain', 'fused'], help='inference path of the headline/e2e numbers: 5-launch chain, single-launch fused kernel, or the faster of the two (both are always measured)')
     ap.add_argument('--pipeline', type=int, default=4, help='ray batches in flight (CUDA streams); 1 = strictly sequential steps')
     args = ap.parse_args()

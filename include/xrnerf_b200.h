@@ -240,6 +240,11 @@ int xrb_nerf_posenc_tiles_rays(const float *rays_o, const float *rays_d, const f
 int xrb_mip_embed(const float *z_vals, const float *rays_o, const float *rays_d, const float *radii, const float *viewdirs, int n_rays, int n_samples, int min_deg_point,
                   int max_deg_point, int min_deg_view, int max_deg_view, float *embedded, float *means_out, float *covs_out, void *stream);
 
+/* The same cast_rays + IPE + view-direction encoding written straight into the fp16 tile image xrb_nerf_mlp_forward_v2 consumes
+ * (xrb_nerf_enc_image_bytes(N*S, 6*(max_deg_point-min_deg_point)) bytes): no fp32 `embedded` round trip. Values are the fp16 roundings of xrb_mip_embed's. */
+int xrb_mip_ipe_tiles_rays(const float *z_vals, const float *rays_o, const float *rays_d, const float *radii, const float *viewdirs, int64_t n_rays, int n_samples, int min_deg_point,
+                           int max_deg_point, int min_deg_view, int max_deg_view, void *enc_image, void *stream);
+
 /* Mip-NeRF resample_along_rays / sorted_piecewise_constant_pdf (networks/utils/mip.py:7-63,:146-176): weights f32[N,S], z_vals f32[N,S+1]
  * -> z_out f32[N,S+1]; u f32[N,S+1] optional (NULL = the deterministic linspace of randomized=False). */
 int xrb_mip_resample(const float *z_vals, const float *weights, const float *u, int n_rays, int n_samples, float resample_padding, float *z_out, void *stream);

@@ -85,3 +85,49 @@ def test_weight_repack_on_update():
         mlp.rgb_linear.bias.add_(1.0)
         b = mlp({'pts': pts, 'viewdirs': vd})['raw']
     assert torch.allclose(b[..., :3], a[..., :3] + 1.0, atol=1e-5) and torch.equal(a[..., 3], b[..., 3])
+
+
+MIP_MODEL = dict(type='MipNerfNetwork', cfg=dict(phase='test', ray_shape='cone', resample_padding=0.01, use_multiscale=False, coarse_loss_mult=0.1, num_levels=2, chunk=800, bs_data='rays_o'),
+                 mlp=MIP_MLP, render=dict(type='MipNerfRender', white_bkgd=True, raw_noise_std=0, rgb_padding=0.001, density_bias=-1, density_activation='softplus'))
+
+
+def _mip_rays(n, seed):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    d = torch.randn((n, 3), device='cuda', generator=g)
+    o = torch.rand((n, 3), device='cuda', generator=g) * 0.2
+    return o, d, torch.nn.functional.normalize(d, dim=-1), torch.full((n, 1), 1.2e-3, device='cuda')
+
+
+def test_mip_ipe_tile_image_is_the_fp16_rounding_of_mip_embed():
+    """xrb_mip_ipe_tiles_rays == xrb_nerf_pack_embedded(xrb_mip_embed(...)) byte for byte (same fp32 expressions, one fp16 rounding); ragged last tile."""
+    from xrnerf_b200 import _C
+    n, s = 37, 19                         # 703 rows: 5 full tiles + a ragged one
+    o, d, vd, radii = _mip_rays(n, 4)
+    z = (2.0 + 4.0 * torch.rand((n, s + 1), device='cuda')).sort(dim=-1).values.contiguous()
+    emb = torch.empty((n * s, 123), device='cuda')
+    _C.check(_C.lib.xrb_mip_embed(_C.ptr(z), _C.ptr(o), _C.ptr(d), _C.ptr(radii.reshape(-1)), _C.ptr(vd), n, s, 0, 16, 0, 4, _C.ptr(emb), None, None, _C.stream()))
+    nbytes = _C.lib.xrb_nerf_enc_image_bytes(n * s, 96)
+    a = torch.zeros(nbytes, dtype=torch.uint8, device='cuda'); b = torch.full((nbytes,), 0xA5, dtype=torch.uint8, device='cuda')
+    _C.check(_C.lib.xrb_nerf_pack_embedded(_C.ptr(emb), n * s, 96, 27, _C.ptr(a), _C.stream()))
+    _C.check(_C.lib.xrb_mip_ipe_tiles_rays(_C.ptr(z), _C.ptr(o), _C.ptr(d), _C.ptr(radii.reshape(-1)), _C.ptr(vd), n, s, 0, 16, 0, 4, _C.ptr(b), _C.stream()))
+    assert nbytes == 6 * 3 * 16384 and torch.equal(a, b)
+
+
+def test_fused_mip_renderer_matches_registry_network():
+    """MipNerfRenderer (IPE tile images -> tcgen05 MLP -> composite, 2 levels) vs MipNerfNetwork.forward(is_test=True) with the fp32 library-GEMM MLP.
+    Tolerance: fp16-operand MLP over 12 layers, then two composites and a resampling that moves with the coarse weights: rgb 1e-2."""
+    from xrnerf_b200 import registry as R
+    from xrnerf_b200.nerf import MipNerfRenderer
+    torch.manual_seed(5)
+    net = R.build_network(MIP_MODEL).cuda()
+    n, S = 200, 128
+    o, d, vd, radii = _mip_rays(n, 6)
+    with torch.no_grad():
+        got = MipNerfRenderer(net, near=2.0, far=6.0, n_samples=S).render(o, d, vd, radii)
+        t = torch.linspace(0., 1., S + 1, device='cuda')
+        data = dict(rays_o=o, rays_d=d, viewdirs=vd, radii=radii, z_vals=(2.0 * (1. - t) + 6.0 * t).expand(n, S + 1).contiguous())
+        net.mlp.fused = False
+        ref = net.forward(data, is_test=True)
+    assert set(got) == set(ref) == {'rgb', 'disp', 'acc', 'coarse_rgb', 'coarse_disp', 'coarse_acc'}
+    for k in ('rgb', 'coarse_rgb', 'acc', 'coarse_acc'):
+        assert (got[k] - ref[k]).abs().max().item() <= 1e-2, k

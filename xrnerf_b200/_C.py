@@ -72,6 +72,7 @@ _SIGS = {
     'xrb_nerf_posenc_tiles': (_i, [P, P, _i64, _i, _i, _i, P, P]),
     'xrb_nerf_posenc_tiles_rays': (_i, [P, P, P, P, _i64, _i, _i, _i, P, P]),
     'xrb_mip_embed': (_i, [P, P, P, P, P, _i, _i, _i, _i, _i, _i, P, P, P, P]),
+    'xrb_mip_ipe_tiles_rays': (_i, [P, P, P, P, P, _i64, _i, _i, _i, _i, _i, P, P]),
     'xrb_mip_resample': (_i, [P, P, P, _i, _i, _f, P, P]),
     'xrb_nerf_get_rays': (_i, [C.POINTER(C.c_float), _i, _i, _f, _f, _f, _f, _i, P, _i64, P, P, P, P, P]),
     'xrb_nerf_zvals': (_i, [_i64, _i, _f, _f, _i, P, P, P]),

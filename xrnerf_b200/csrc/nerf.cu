@@ -250,6 +250,69 @@ __global__ void __launch_bounds__(256) mip_embed_kernel(int n_rays, int S, int m
     }
 }
 
+// The same cast_rays + IPE + view-direction encoding written straight into the fp16 UMMA tile images the tcgen05 NerfMLP kernel TMA-loads
+// (csrc/nerf_mlp_tc.cu: per 128-row tile, point blocks [128 x 64] x 2 (96 -> 128 columns, zero padded), then the direction block; K-major,
+// 128-byte swizzle): no fp32 `embedded` [N*S,123] round trip (63 GB per 800x800 image in the reference). One thread per (row, 16-byte chunk);
+// the frustum Gaussian is formed once per thread in registers. Values are the fp16 roundings of exactly what mip_embed_kernel produces.
+__device__ __forceinline__ uint32_t ipe_sw128(uint32_t row, uint32_t chunk16) { return (row >> 3) * 1024u + (row & 7u) * 128u + ((chunk16 ^ (row & 7u)) << 4); }
+__device__ __forceinline__ uint32_t ipe_pack_h2(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t *>(&h); }
+__global__ void __launch_bounds__(256) mip_ipe_tiles_kernel(int64_t n_rays, int S, int min_deg, int max_deg, int min_deg_view, int max_deg_view, const float *__restrict__ z_vals,
+                                                            const float *__restrict__ rays_o, const float *__restrict__ rays_d, const float *__restrict__ radii,
+                                                            const float *__restrict__ viewdirs, uint8_t *__restrict__ image) {
+    const int n_deg = max_deg - min_deg, n_deg_v = max_deg_view - min_deg_view;
+    const int c_ipe = 6 * n_deg, c_dir = 3 + 6 * n_deg_v, aux = (c_ipe + 63) / 64, chunks_per_row = (aux + 1) * 8;
+    const int64_t n_rows = n_rays * S, n_tiles = (n_rows + 127) / 128, total = n_tiles * 128 * chunks_per_row;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / chunks_per_row; const int cc = (int)(idx - row * chunks_per_row);
+        const int blk = cc >> 3, ch = cc & 7;
+        const bool is_dir = blk == aux, live = row < n_rows;
+        const int width = is_dir ? c_dir : c_ipe, k0 = (is_dir ? 0 : blk * 64) + ch * 8;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = 0.f;
+        if (live && k0 < width) {
+            const int64_t ray = row / S; const int k = (int)(row - ray * S);
+            if (!is_dir) {
+                const float d[3] = {rays_d[3 * ray], rays_d[3 * ray + 1], rays_d[3 * ray + 2]};
+                const float o[3] = {rays_o[3 * ray], rays_o[3 * ray + 1], rays_o[3 * ray + 2]};
+                const float dmag = fmaxf(1e-10f, d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                float mean[3], cov[3];
+                frustum_gaussian(z_vals[ray * (S + 1) + k], z_vals[ray * (S + 1) + k + 1], radii[ray], d, o, dmag, mean, cov);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int c = k0 + q;
+                    if (c < c_ipe) {
+                        const int qq = c < c_ipe / 2 ? c : c - c_ipe / 2;
+                        const int deg = qq / 3 + min_deg, ax = qq % 3;
+                        const float sc = exp2f((float)deg);
+                        float y = (ax == 0 ? mean[0] : ax == 1 ? mean[1] : mean[2]) * sc;
+                        const float yv = (ax == 0 ? cov[0] : ax == 1 ? cov[1] : cov[2]) * sc * sc;
+                        if (c >= c_ipe / 2) y += 1.5707963267948966f;
+                        v[q] = expf(-0.5f * yv) * sinf(y);
+                    }
+                }
+            } else {
+                const float vd[3] = {viewdirs[3 * ray], viewdirs[3 * ray + 1], viewdirs[3 * ray + 2]};
+                const int halfn = 3 * n_deg_v;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int c = k0 + q;
+                    if (c < 3) v[q] = c == 0 ? vd[0] : c == 1 ? vd[1] : vd[2];
+                    else if (c < c_dir) {
+                        const int qd = c - 3, qq = qd < halfn ? qd : qd - halfn, ax = qq % 3;
+                        float x = (ax == 0 ? vd[0] : ax == 1 ? vd[1] : vd[2]) * exp2f((float)(qq / 3 + min_deg_view));
+                        if (qd >= halfn) x += 1.5707963267948966f;
+                        v[q] = sinf(x);
+                    }
+                }
+            }
+        }
+        const int64_t tile = row >> 7; const uint32_t r = (uint32_t)(row & 127);
+        *reinterpret_cast<uint4 *>(image + ((size_t)tile * (aux + 1) + blk) * 16384 + ipe_sw128(r, ch)) =
+            make_uint4(ipe_pack_h2(v[0], v[1]), ipe_pack_h2(v[2], v[3]), ipe_pack_h2(v[4], v[5]), ipe_pack_h2(v[6], v[7]));
+    }
+}
+
 // Mip-NeRF resample_along_rays + sorted_piecewise_constant_pdf (networks/utils/mip.py:146-176, :7-63), randomized=False or
 // caller-supplied jitter: one warp per ray, O(S log S) interval search instead of the reference's [N,S+2,S+1] mask.
 constexpr int MIP_MAX_S = 256;
@@ -412,6 +475,19 @@ int xrb_mip_embed(const float *z_vals, const float *rays_o, const float *rays_d,
     mip_embed_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n_rays, n_samples, min_deg_point, max_deg_point, min_deg_view, max_deg_view, z_vals, rays_o, rays_d, radii, viewdirs, embedded,
                                                                    means_out, covs_out);
     return check_launch("mip_embed");
+}
+
+int xrb_mip_ipe_tiles_rays(const float *z_vals, const float *rays_o, const float *rays_d, const float *radii, const float *viewdirs, int64_t n_rays, int n_samples, int min_deg_point,
+                           int max_deg_point, int min_deg_view, int max_deg_view, void *enc_image, void *stream) {
+    XRB_REQUIRE(n_rays >= 0 && n_samples >= 1 && max_deg_point > min_deg_point && max_deg_view >= min_deg_view, "mip_ipe_tiles_rays: bad size");
+    XRB_REQUIRE(6 * (max_deg_point - min_deg_point) <= 128 && 3 + 6 * (max_deg_view - min_deg_view) <= 64, "mip_ipe_tiles_rays: encoding wider than the tile image (128 + 64 columns)");
+    if (n_rays == 0) return XRB_OK;
+    XRB_REQUIRE(z_vals && rays_o && rays_d && radii && viewdirs && enc_image && ((uintptr_t)enc_image & 15) == 0, "mip_ipe_tiles_rays: null/misaligned pointer");
+    const int aux = (6 * (max_deg_point - min_deg_point) + 63) / 64;
+    int64_t total = ((n_rays * n_samples + 127) / 128) * 128 * (aux + 1) * 8, blocks = (total + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
+    mip_ipe_tiles_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n_rays, n_samples, min_deg_point, max_deg_point, min_deg_view, max_deg_view, z_vals, rays_o, rays_d, radii, viewdirs,
+                                                                       (uint8_t *)enc_image);
+    return check_launch("mip_ipe_tiles_rays");
 }
 
 int xrb_mip_resample(const float *z_vals, const float *weights, const float *u, int n_rays, int n_samples, float resample_padding, float *z_out, void *stream) {
