@@ -225,6 +225,9 @@ int xrb_nerf_mlp_forward(const void *weight_image, const float *bias, const floa
 /* v2 of the same kernel: two epilogue warpgroups per tile, phased MMA issue, double-buffered TMEM accumulators, half-slab weight stream
  * (image/bias from xrnerf_b200.nerf_mlp.pack_nerf_mlp_v2) */
 int xrb_nerf_mlp_forward_v2(const void *weight_image, const float *bias, const void *enc_image, int64_t n_rows, int input_ch, int input_ch_dirs, float *raw, void *stream);
+/* v3 of the same chain (csrc/nerf_mlp_tc3.cu): two 128-row tiles in flight per SM so the tensor core runs one tile's layer while the other tile's
+ * accumulators are drained. weight_image / bias from the matching host packer (xrnerf_b200.nerf_mlp.pack_nerf_mlp_v3: bias = fp32 vector + fp16 copy). */
+int xrb_nerf_mlp_forward_v3(const void *weight_image, const float *bias, const void *enc_image, int64_t n_rows, int input_ch, int input_ch_dirs, float *raw, void *stream);
 /* encoding tile image consumed by v2 (per 128-row tile: point-encoding block(s) then direction block, [128x64] fp16, UMMA K-major 128B swizzle):
  * size, conversion from an fp32 `embedded` matrix, and BaseEmbedder's positional encoding written directly in that form */
 size_t xrb_nerf_enc_image_bytes(int64_t n_rows, int input_ch);

@@ -98,7 +98,7 @@ def _mip_rays(n, seed):
     return o, d, torch.nn.functional.normalize(d, dim=-1), torch.full((n, 1), 1.2e-3, device='cuda')
 
 
-def test_mip_ipe_tile_image_is_the_fp16_rounding_of_mip_embed():
+def test_mip_ipe_tile_image_is_the_fp16_rounding_of_mip_embed(monkeypatch):
     """xrb_mip_ipe_tiles_rays == xrb_nerf_pack_embedded(xrb_mip_embed(...)) byte for byte (same fp32 expressions, one fp16 rounding); ragged last tile."""
     from xrnerf_b200 import _C
     n, s = 37, 19                         # 703 rows: 5 full tiles + a ragged one
@@ -110,7 +110,43 @@ def test_mip_ipe_tile_image_is_the_fp16_rounding_of_mip_embed():
     a = torch.zeros(nbytes, dtype=torch.uint8, device='cuda'); b = torch.full((nbytes,), 0xA5, dtype=torch.uint8, device='cuda')
     _C.check(_C.lib.xrb_nerf_pack_embedded(_C.ptr(emb), n * s, 96, 27, _C.ptr(a), _C.stream()))
     _C.check(_C.lib.xrb_mip_ipe_tiles_rays(_C.ptr(z), _C.ptr(o), _C.ptr(d), _C.ptr(radii.reshape(-1)), _C.ptr(vd), n, s, 0, 16, 0, 4, _C.ptr(b), _C.stream()))
-    assert nbytes == 6 * 3 * 16384 and torch.equal(a, b)
+    assert nbytes == 6 * 3 * 16384
+    assert torch.equal(a.view(torch.float16), b.view(torch.float16))      # as fp16 VALUES: where exp(-y_var/2) < 2^-25 the specialised kernel writes +0 without evaluating sin (may be -0 above)
+    monkeypatch.setenv('XRB_GENERIC_ENCODERS', '1')                        # the generic-degree kernel: byte for byte
+    c = torch.full((nbytes,), 0x5A, dtype=torch.uint8, device='cuda')
+    _C.check(_C.lib.xrb_mip_ipe_tiles_rays(_C.ptr(z), _C.ptr(o), _C.ptr(d), _C.ptr(radii.reshape(-1)), _C.ptr(vd), n, s, 0, 16, 0, 4, _C.ptr(c), _C.stream()))
+    assert torch.equal(a, c)
+
+
+def test_posenc_tile_images_match_fp32_posenc(monkeypatch):
+    """xrb_nerf_posenc_tiles / _rays (specialised multires 10/4 kernel and the generic one) == fp16 rounding of xrb_nerf_posenc on pts = o + d*z formed
+    by torch (GetPts). The specialised kernel uses sincosf where the fp32 kernel uses sinf / cosf: allow 1 fp16 ulp on < 0.1 % of the entries."""
+    from xrnerf_b200 import _C
+    n, s = 29, 21
+    g = torch.Generator(device='cuda').manual_seed(9)
+    o = torch.rand((n, 3), device='cuda', generator=g); d = torch.randn((n, 3), device='cuda', generator=g)
+    vd = torch.nn.functional.normalize(d, dim=-1)
+    z = (2.0 + 4.0 * torch.rand((n, s), device='cuda', generator=g)).sort(dim=-1).values.contiguous()
+    pts = (o[:, None, :] + d[:, None, :] * z[:, :, None]).contiguous()
+    emb = torch.empty((n * s, 90), device='cuda')
+    _C.check(_C.lib.xrb_nerf_posenc(_C.ptr(pts), _C.ptr(vd), n * s, s, 10, 4, _C.ptr(emb), _C.stream()))
+    nbytes = _C.lib.xrb_nerf_enc_image_bytes(n * s, 63)
+    ref = torch.zeros(nbytes, dtype=torch.uint8, device='cuda')
+    _C.check(_C.lib.xrb_nerf_pack_embedded(_C.ptr(emb), n * s, 63, 27, _C.ptr(ref), _C.stream()))
+    ref16 = ref.view(torch.float16).float()
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv('XRB_GENERIC_ENCODERS', '1')
+        for ray_mode in (False, True):
+            img = torch.full((nbytes,), 0xA5, dtype=torch.uint8, device='cuda')
+            if ray_mode:
+                _C.check(_C.lib.xrb_nerf_posenc_tiles_rays(_C.ptr(o), _C.ptr(d), _C.ptr(z), _C.ptr(vd), n, s, 10, 4, _C.ptr(img), _C.stream()))
+            else:
+                _C.check(_C.lib.xrb_nerf_posenc_tiles(_C.ptr(pts), _C.ptr(vd), n * s, s, 10, 4, _C.ptr(img), _C.stream()))
+            got = img.view(torch.float16).float()
+            diff = (got - ref16).abs()
+            assert diff.max().item() <= 1e-3, (generic, ray_mode)             # one fp16 ulp below 1.0 is 4.9e-4
+            assert (diff > 0).float().mean().item() <= (0.0 if generic else 1e-3), (generic, ray_mode)
 
 
 def test_fused_mip_renderer_matches_registry_network():
@@ -131,3 +167,25 @@ def test_fused_mip_renderer_matches_registry_network():
     assert set(got) == set(ref) == {'rgb', 'disp', 'acc', 'coarse_rgb', 'coarse_disp', 'coarse_acc'}
     for k in ('rgb', 'coarse_rgb', 'acc', 'coarse_acc'):
         assert (got[k] - ref[k]).abs().max().item() <= 1e-2, k
+
+
+@pytest.mark.parametrize('cfg,n_rows', [(NERF_MLP, 1), (NERF_MLP, 129), (NERF_MLP, 2 * 296 * 128 + 77), (MIP_MLP, 128), (MIP_MLP, 2 * 296 * 128 + 300)])
+def test_nerf_mlp_v3_two_tiles_in_flight_matches_v2_and_fp32(cfg, n_rows, monkeypatch):
+    """csrc/nerf_mlp_tc3.cu (two tile pipelines per SM, AUX block time-shared by point / direction encodings, several tiles per pipeline at the
+    larger sizes) against v2 (same fp16 arithmetic in the same K order: <= 1e-3 of max|raw|, normally bit-identical) and the fp32 library path (2e-2)."""
+    from xrnerf_b200 import registry as R
+    from xrnerf_b200.nerf_mlp import nerf_mlp_forward
+    torch.manual_seed(7)
+    mlp = R.build_mlp(cfg).cuda()
+    emb = torch.randn((n_rows, mlp.input_ch + mlp.input_ch_dirs), device='cuda').clamp_(-1, 1)
+    out = {}
+    for v in ('2', '3'):
+        monkeypatch.setenv('XRB_NERF_MLP_V', v)
+        image, bias = mlp._packed()
+        out[v] = nerf_mlp_forward(image, bias, emb, mlp.input_ch, mlp.input_ch_dirs, version=int(v)).clone()
+    torch.cuda.synchronize()
+    scale = out['2'].abs().max().item()
+    assert (out['3'] - out['2']).abs().max().item() <= 1e-3 * scale + 1e-6
+    with torch.no_grad():
+        ref = _ref_fp32(mlp, emb[:4096])
+    assert (out['3'][:4096] - ref).abs().max().item() <= 2e-2 * ref.abs().max().item() + 1e-3

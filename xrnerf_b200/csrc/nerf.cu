@@ -2,6 +2,7 @@
 // render call, a full sort + expanded gathers per sample_pdf call): one launch each, one WARP per ray,
 // lanes over samples with shuffle scans. References relative to /root/reference/xrnerf/models/.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace xrb {
 
@@ -313,6 +314,122 @@ __global__ void __launch_bounds__(256) mip_ipe_tiles_kernel(int64_t n_rays, int 
     }
 }
 
+// ---- fast tile-image encoders for the reference configurations (thread == (tile, encoding block, row): a warp works on 32 rows of ONE block
+// kind, so there is no intra-warp divergence; every trig evaluation is shared by the columns that use it and all column indices are compile-time).
+// The generic kernels above / in nerf_mlp_tc.cu stay as the fallback for other degrees. Launch list before this change (gpurun_out, 32768 rays):
+// mip_ipe_tiles_kernel 4.29 ms per 4.2 M rows and posenc_tiles_kernel 1.92 ms per 6.3 M rows next to 8.46 ms of MLP.
+__device__ __forceinline__ float pow2i(int e) { return __int_as_float((127 + e) << 23); }   // 2^e, exact, -126 <= e <= 127
+__device__ __forceinline__ void store_chunk(uint8_t *blk_row, uint32_t chunk, uint32_t r7, const float *v) {
+    *reinterpret_cast<uint4 *>(blk_row + ((chunk ^ r7) << 4)) = make_uint4(ipe_pack_h2(v[0], v[1]), ipe_pack_h2(v[2], v[3]), ipe_pack_h2(v[4], v[5]), ipe_pack_h2(v[6], v[7]));
+}
+// Mip-NeRF, 6*NDEG <= 128 point columns (two blocks) + direction block. item 0 = both point blocks of the row, item 1 = direction block.
+// IPE column q (< 3*NDEG): exp(-0.5 * cov_ax * 4^deg) * sin(mean_ax * 2^deg), column 3*NDEG + q: the same with sin(y + pi/2) — the reference's
+// expression, NOT cos(y): fl(y + pi/2) differs from y + pi/2 by up to ulp(y)/2 and the reference's value includes that (mipnerf_embedder.py:35-41,:55-60).
+// |value| <= exp(-0.5 y_var) < 2^-25 rounds to (+-)0 in fp16, so the trig evaluation is skipped when 0.5 * y_var > 20.
+template <int NDEG, int NDEGV>
+__global__ void __launch_bounds__(256) mip_ipe_tiles_fast_kernel(int64_t n_rays, int S, int min_deg, int min_deg_view, const float *__restrict__ z_vals, const float *__restrict__ rays_o,
+                                                                 const float *__restrict__ rays_d, const float *__restrict__ radii, const float *__restrict__ viewdirs, uint8_t *__restrict__ image) {
+    static_assert(3 * NDEG % 8 == 0 && 6 * NDEG > 64 && 6 * NDEG <= 128 && 3 + 6 * NDEGV <= 64, "tile-image geometry");
+    constexpr int HALF = 3 * NDEG, NJ = HALF / 8;
+    const int64_t n_rows = n_rays * S, n_tiles = (n_rows + 127) / 128, total = n_tiles * 256;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(idx & 127); const int item = (int)((idx >> 7) & 1); const int64_t tile = idx >> 8;
+        const int64_t row = tile * 128 + r;
+        const bool live = row < n_rows;
+        const uint32_t r7 = r & 7u;
+        uint8_t *trow = image + (size_t)tile * 3 * 16384 + (r >> 3) * 1024u + r7 * 128u;     // my row inside block 0 of the tile
+        const int64_t ray = live ? row / S : 0; const int k = (int)(row - ray * S);
+        if (item == 0) {
+            float mean[3] = {0.f, 0.f, 0.f}, cov[3] = {0.f, 0.f, 0.f};
+            if (live) {
+                const float d[3] = {rays_d[3 * ray], rays_d[3 * ray + 1], rays_d[3 * ray + 2]};
+                const float o[3] = {rays_o[3 * ray], rays_o[3 * ray + 1], rays_o[3 * ray + 2]};
+                const float dmag = fmaxf(1e-10f, d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                frustum_gaussian(z_vals[ray * (S + 1) + k], z_vals[ray * (S + 1) + k + 1], radii[ray], d, o, dmag, mean, cov);
+            }
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                float sv[8], cv[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int q = 8 * j + e, deg = q / 3, ax = q % 3;
+                    const float sc = pow2i(deg + min_deg);
+                    const float y = mean[ax] * sc, hv = 0.5f * (cov[ax] * sc * sc);
+                    float s = 0.f, c = 0.f;
+                    if (live && hv <= 20.f) { const float ex = expf(-hv); s = ex * sinf(y); c = ex * sinf(y + 1.5707963267948966f); }
+                    sv[e] = s; cv[e] = c;
+                }
+                store_chunk(trow, j, r7, sv);                                                   // columns 8j .. 8j+7 of block 0
+                const int cc = HALF + 8 * j;                                                    // first "cos" column of this group
+                store_chunk(trow + (cc >> 6) * 16384, (uint32_t)(cc & 63) >> 3, r7, cv);
+            }
+            const float z8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int ch = (6 * NDEG - 64) / 8; ch < 8; ++ch) store_chunk(trow + 16384, ch, r7, z8);   // zero padding of block 1
+        } else {
+            float v[64];
+#pragma unroll
+            for (int e = 0; e < 64; ++e) v[e] = 0.f;
+            if (live) {
+                const float vd[3] = {viewdirs[3 * ray], viewdirs[3 * ray + 1], viewdirs[3 * ray + 2]};
+#pragma unroll
+                for (int a = 0; a < 3; ++a) v[a] = vd[a];
+#pragma unroll
+                for (int q = 0; q < 3 * NDEGV; ++q) {
+                    const float x = vd[q % 3] * pow2i(q / 3 + min_deg_view);
+                    v[3 + q] = sinf(x); v[3 + 3 * NDEGV + q] = sinf(x + 1.5707963267948966f);
+                }
+            }
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) store_chunk(trow + 2 * 16384, ch, r7, v + 8 * ch);
+        }
+    }
+}
+
+// BaseEmbedder (embedders/base.py:26-52), 3 + 6*LP <= 64 point columns (one block) + direction block; item 0 = point block, item 1 = direction block.
+// column 3 + 6b + a = sin(2^b x_a), column 3 + 6b + 3 + a = cos(2^b x_a). ray mode as posenc_tiles_kernel (rays_o != NULL: `pts` is z_vals).
+template <int LP, int LD>
+__global__ void __launch_bounds__(256) posenc_tiles_fast_kernel(const float *__restrict__ pts, const float *__restrict__ viewdirs, int64_t n_rows, int samples_per_ray,
+                                                                uint8_t *__restrict__ image, const float *__restrict__ rays_o, const float *__restrict__ rays_d) {
+    static_assert(3 + 6 * LP <= 64 && 3 + 6 * LD <= 64, "one block each");
+    const int64_t n_tiles = (n_rows + 127) / 128, total = n_tiles * 256;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(idx & 127); const int item = (int)((idx >> 7) & 1); const int64_t tile = idx >> 8;
+        const int64_t row = tile * 128 + r;
+        const bool live = row < n_rows;
+        const uint32_t r7 = r & 7u;
+        uint8_t *trow = image + ((size_t)tile * 2 + item) * 16384 + (r >> 3) * 1024u + r7 * 128u;
+        float v[64];
+#pragma unroll
+        for (int e = 0; e < 64; ++e) v[e] = 0.f;
+        if (live) {
+            float x[3];
+            const int64_t ray = row / samples_per_ray;
+            if (item == 1) { x[0] = viewdirs[3 * ray]; x[1] = viewdirs[3 * ray + 1]; x[2] = viewdirs[3 * ray + 2]; }
+            else if (rays_o) {
+                const float z = pts[row];
+                // GetPts (create.py:588-597): o + d * z as a rounded product then a rounded sum (torch), never an FMA — the 2^9-scaled sin arguments amplify the difference
+                x[0] = __fadd_rn(rays_o[3 * ray], __fmul_rn(rays_d[3 * ray], z)); x[1] = __fadd_rn(rays_o[3 * ray + 1], __fmul_rn(rays_d[3 * ray + 1], z)); x[2] = __fadd_rn(rays_o[3 * ray + 2], __fmul_rn(rays_d[3 * ray + 2], z));
+            } else { x[0] = pts[3 * row]; x[1] = pts[3 * row + 1]; x[2] = pts[3 * row + 2]; }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) v[a] = x[a];
+            if (item == 0) {
+#pragma unroll
+                for (int bnd = 0; bnd < LP; ++bnd)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) { float sn, cs; sincosf(x[a] * pow2i(bnd), &sn, &cs); v[3 + 6 * bnd + a] = sn; v[6 + 6 * bnd + a] = cs; }
+            } else {
+#pragma unroll
+                for (int bnd = 0; bnd < LD; ++bnd)
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) { float sn, cs; sincosf(x[a] * pow2i(bnd), &sn, &cs); v[3 + 6 * bnd + a] = sn; v[6 + 6 * bnd + a] = cs; }
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) store_chunk(trow, ch, r7, v + 8 * ch);
+    }
+}
+
 // Mip-NeRF resample_along_rays + sorted_piecewise_constant_pdf (networks/utils/mip.py:146-176, :7-63), randomized=False or
 // caller-supplied jitter: one warp per ray, O(S log S) interval search instead of the reference's [N,S+2,S+1] mask.
 constexpr int MIP_MAX_S = 256;
@@ -485,9 +602,22 @@ int xrb_mip_ipe_tiles_rays(const float *z_vals, const float *rays_o, const float
     XRB_REQUIRE(z_vals && rays_o && rays_d && radii && viewdirs && enc_image && ((uintptr_t)enc_image & 15) == 0, "mip_ipe_tiles_rays: null/misaligned pointer");
     const int aux = (6 * (max_deg_point - min_deg_point) + 63) / 64;
     int64_t total = ((n_rays * n_samples + 127) / 128) * 128 * (aux + 1) * 8, blocks = (total + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
+    if (max_deg_point - min_deg_point == 16 && max_deg_view - min_deg_view == 4 && min_deg_point >= -100 && max_deg_point <= 100 && min_deg_view >= -100 && max_deg_view <= 100 &&
+        !getenv("XRB_GENERIC_ENCODERS")) {                     // the reference configuration (configs/mipnerf/*.py): specialised kernel
+        int64_t items = ((n_rays * n_samples + 127) / 128) * 256, fb = (items + 255) / 256; if (fb > NUM_SMS * 16) fb = NUM_SMS * 16;
+        mip_ipe_tiles_fast_kernel<16, 4><<<(int)fb, 256, 0, (cudaStream_t)stream>>>(n_rays, n_samples, min_deg_point, min_deg_view, z_vals, rays_o, rays_d, radii, viewdirs, (uint8_t *)enc_image);
+        return check_launch("mip_ipe_tiles_rays");
+    }
     mip_ipe_tiles_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(n_rays, n_samples, min_deg_point, max_deg_point, min_deg_view, max_deg_view, z_vals, rays_o, rays_d, radii, viewdirs,
                                                                        (uint8_t *)enc_image);
     return check_launch("mip_ipe_tiles_rays");
+}
+
+// called by xrb_nerf_posenc_tiles / xrb_nerf_posenc_tiles_rays (nerf_mlp_tc.cu) for the reference configuration multires=10, multires_dirs=4
+int xrb_internal_posenc_tiles_fast(const float *pts, const float *viewdirs, int64_t n_rows, int samples_per_ray, void *enc_image, const float *rays_o, const float *rays_d, void *stream) {
+    int64_t items = ((n_rows + 127) / 128) * 256, fb = (items + 255) / 256; if (fb > NUM_SMS * 16) fb = NUM_SMS * 16;
+    posenc_tiles_fast_kernel<10, 4><<<(int)fb, 256, 0, (cudaStream_t)stream>>>(pts, viewdirs, n_rows, samples_per_ray, (uint8_t *)enc_image, rays_o, rays_d);
+    return check_launch("posenc_tiles");
 }
 
 int xrb_mip_resample(const float *z_vals, const float *weights, const float *u, int n_rays, int n_samples, float resample_padding, float *z_out, void *stream) {

@@ -122,23 +122,72 @@ def pack_nerf_mlp_v2(mlp):
     return torch.from_numpy(np.concatenate(slabs)).to(dev), torch.from_numpy(np.concatenate(biases)).to(dev)
 
 
+def pack_nerf_mlp_v3(mlp):
+    """Image for csrc/nerf_mlp_tc3.cu: half slabs ([N/n_halves x 64]) in the kernel's stream order — per layer, per K-block (AUX block first where a layer
+    reads it), output half 0 then 1. Bias vector: fp32 per-layer biases, Wa[256], ba, padded to 8 floats, then an fp16 copy of the per-layer biases."""
+    assert len(mlp.pts_linears) == 8 and list(mlp.skips) == [4] and mlp.use_viewdirs and mlp.pts_linears[0].out_features == 256
+    ic, icd = mlp.input_ch, mlp.input_ch_dirs
+    aux = (ic + 63) // 64
+    assert aux in (1, 2)
+    g = lambda lin: (lin.weight.detach().float().cpu().numpy(), lin.bias.detach().float().cpu().numpy())
+    H = lambda W, j, off=0: _pad_cols(W, off + 64 * j, off + 64 * (j + 1))
+    layers = []   # (column blocks in K order, N, n_halves, bias)
+    W, b = g(mlp.pts_linears[0])
+    layers.append(([_pad_cols(W, 64 * j, 64 * (j + 1)) for j in range(aux)], 256, 2, b))          # AUX (pts block 0) [, H3 = pts block 1]
+    for l in range(1, 8):
+        W, b = g(mlp.pts_linears[l])
+        if l == 5:   # input = cat([pts(ic), h(256)])
+            Wp = W[:, :ic]
+            blocks = [_pad_cols(Wp, 0, 64)] + [H(W, j, ic) for j in range(4)] + ([_pad_cols(Wp, 64, 128)] if aux == 2 else [])
+        else:
+            blocks = [H(W, j) for j in range(4)]
+        layers.append((blocks, 256, 2, b))
+    W, b = g(mlp.feature_linear)
+    layers.append(([H(W, j) for j in range(4)], 256, 2, b))
+    W, b = g(mlp.views_linears[0])                                                                 # [128, 256 + icd] on cat([feature, dirs]); direction block first
+    layers.append(([_pad_cols(W[:, 256:], 0, 64)] + [H(W, j) for j in range(4)], 128, 1, b))
+    Wr, br = g(mlp.rgb_linear)
+    W16 = np.zeros((16, 128), np.float32); W16[:3] = Wr
+    layers.append(([H(W16, 0), H(W16, 1)], 16, 1, np.concatenate([br, np.zeros(13, np.float32)])))
+    slabs, biases = [], []
+    for blocks, N, nh, b in layers:
+        hw = N // nh
+        for blk in blocks:
+            assert blk.shape == (N, 64)
+            for half in range(nh):
+                slabs.append(_slab(blk[half * hw:(half + 1) * hw]))
+        biases.append(b.astype(np.float32))
+    layer_bias = np.concatenate(biases)
+    Wa, ba = g(mlp.alpha_linear)
+    f32 = np.concatenate([layer_bias, Wa[0].astype(np.float32), ba.astype(np.float32)])
+    f32 = np.concatenate([f32, np.zeros((-len(f32)) % 8, np.float32)])
+    h16 = layer_bias.astype(np.float16)
+    h16 = np.concatenate([h16, np.zeros((-len(h16)) % 8, np.float16)])
+    dev = mlp.pts_linears[0].weight.device
+    return torch.from_numpy(np.concatenate(slabs)).to(dev), torch.from_numpy(np.concatenate([f32, h16.view(np.float32)])).to(dev)
+
+
 def nerf_mlp_forward(image, bias, embedded, input_ch, input_ch_dirs, version=1):
     _C.require_cuda(image, bias, embedded)
     embedded = embedded.contiguous().float()
     n = embedded.shape[0]
     raw = torch.empty((n, 4), dtype=torch.float32, device=embedded.device)
-    if version == 2:   # fp32 embedded -> fp16 tile image (one streaming kernel) -> MLP kernel that TMA-loads it
+    if version >= 2:   # fp32 embedded -> fp16 tile image (one streaming kernel) -> MLP kernel that TMA-loads it
         enc = torch.empty(_C.lib.xrb_nerf_enc_image_bytes(n, int(input_ch)), dtype=torch.uint8, device=embedded.device)
         _C.check(_C.lib.xrb_nerf_pack_embedded(_C.ptr(embedded), n, int(input_ch), int(input_ch_dirs), _C.ptr(enc), _C.stream()), 'nerf_pack_embedded')
-        return nerf_mlp_forward_tiles(image, bias, enc, n, input_ch, input_ch_dirs, raw)
+        return nerf_mlp_forward_tiles(image, bias, enc, n, input_ch, input_ch_dirs, raw, version=version)
     fn = _C.lib.xrb_nerf_mlp_forward
     _C.check(fn(_C.ptr(image), _C.ptr(bias), _C.ptr(embedded), n, int(input_ch), int(input_ch_dirs), _C.ptr(raw), _C.stream()), 'nerf_mlp_forward')
     return raw
 
 
-def nerf_mlp_forward_tiles(image, bias, enc_image, n_rows, input_ch, input_ch_dirs, raw=None):
-    """v2 kernel on an already packed encoding tile image (xrb_nerf_pack_embedded / xrb_nerf_posenc_tiles)."""
+def nerf_mlp_forward_tiles(image, bias, enc_image, n_rows, input_ch, input_ch_dirs, raw=None, version=2):
+    """v2 / v3 kernel on an already packed encoding tile image (xrb_nerf_pack_embedded / xrb_nerf_posenc_tiles / xrb_mip_ipe_tiles_rays);
+    image/bias must come from the matching packer (pack_nerf_mlp_v2 / pack_nerf_mlp_v3)."""
     if raw is None:
         raw = torch.empty((n_rows, 4), dtype=torch.float32, device=enc_image.device)
+    if version == 3:
+        _C.check(_C.lib.xrb_nerf_mlp_forward_v3(_C.ptr(image), _C.ptr(bias), _C.ptr(enc_image), n_rows, int(input_ch), int(input_ch_dirs), _C.ptr(raw), _C.stream()), 'nerf_mlp_forward_v3')
+        return raw
     _C.check(_C.lib.xrb_nerf_mlp_forward_v2(_C.ptr(image), _C.ptr(bias), _C.ptr(enc_image), n_rows, int(input_ch), int(input_ch_dirs), _C.ptr(raw), _C.stream()), 'nerf_mlp_forward_v2')
     return raw

@@ -55,8 +55,8 @@ class NerfMLP(BaseMLP):
         self.kernel_version = int(os.environ.get('XRB_NERF_MLP_V', '2'))
         ver = tuple(p._version for p in self.parameters()) + (self.pts_linears[0].weight.device, self.kernel_version)
         if getattr(self, '_pack_ver', None) != ver:
-            from ..nerf_mlp import pack_nerf_mlp, pack_nerf_mlp_v2
-            self._pack = pack_nerf_mlp_v2(self) if self.kernel_version == 2 else pack_nerf_mlp(self)
+            from ..nerf_mlp import pack_nerf_mlp, pack_nerf_mlp_v2, pack_nerf_mlp_v3
+            self._pack = {1: pack_nerf_mlp, 2: pack_nerf_mlp_v2, 3: pack_nerf_mlp_v3}[self.kernel_version](self)
             self._pack_ver = ver
         return self._pack
 
