@@ -114,8 +114,9 @@ def cpu_reference_rate(sample_rays, reps=1):
             pass
         coords = c[:cnt[1]]
         raw = port.ngp_mlp_forward(table, dens, color, np.ascontiguousarray(coords[:, :3]), np.ascontiguousarray(coords[:, 4:]))
-        m.calc_rgb_inference(raw, coords, ns, np.zeros(3, np.float32))
+        rgb_cpu, alpha_cpu = m.calc_rgb_inference(raw, coords, ns, np.zeros(3, np.float32))
         dt = time.perf_counter() - t0
+        cpu_reference_rate.last = (np.asarray(rgb_cpu).copy(), np.asarray(alpha_cpu).copy(), np.asarray(ns)[:, 0].copy())
         best = dt if best is None else min(best, dt)
         n_samples = int(cnt[1])
     cores = os.cpu_count() or 1
@@ -337,6 +338,43 @@ def run_ours(args):
                  'what': 'march + compaction + field fwd (tcgen05) + composite fwd/bwd + field bwd + grad all-reduce (NCCL, world>1) + fused Adam over 12.2M params',
                  'compacted_samples_per_step': int(tr.cnt_c[1].item())}
 
+    # ---- occupancy-grid update (ngp_grid_sampler.py:90-166; every 16 training steps): candidate cells -> density query -> splat -> EMA -> bitfield + mean
+    grid_upd = None
+    if not args.no_grid:
+        from xrnerf_b200 import registry as R, synth
+        from xrnerf_b200.registry.mlps import HashNerfMLP
+        smp = R.build_sampler(dict(type='NGPGridSampler', update_grid_freq=16, update_block_size=5000000, n_rays_per_batch=4096, cone_angle_constant=0.00390625, near_distance=0.2,
+                                   target_batch_size=1 << 18, rgb_activation=2, density_activation=3))
+        poses = synth.spiral_poses_ngp(40)
+        smp.set_data(dict(poses=poses, focal=np.full((40, 2), synth.FOCAL), aabb_scale=1, aabb_range=(0.0, 1.0), metadata=synth.metadata_for(40)), dict(H=800, W=800))
+        smp.check_device({'rays_o': dev_batches[0][0]})
+
+        class _Density:   # the sampler only needs run_density (hashnerf_mlp.py:107-111)
+            def run_density(self, pts):
+                return field.run_density(pts)
+        dm = _Density()
+        M = 128 ** 3
+        modes = {}
+        for name, (nu, nn_) in (('warmup_phase_uniform_M', (M, 0)), ('steady_quarter_plus_quarter', (M // 4, M // 4))):
+            for _ in range(2):
+                smp.update_density_grid_func(nu, nn_, dm)
+            barrier()
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            KU = 5
+            u0.record()
+            for _ in range(KU):
+                smp.update_density_grid_func(nu, nn_, dm)
+            u1.record()
+            barrier()
+            ms = u0.elapsed_time(u1) / KU
+            n_q = nu + nn_
+            # algorithmic HBM stream: tmp zero-fill 64 MB + EMA read grid+tmp, write grid (192 MB) + bitfield pass reads level grids (64 MB) writes 2 MB
+            # + per candidate 12+4 B written and read, 4 B density, 4 B splat atomic; the density query's gathers (512 B/cell) are L2 traffic
+            stream_bytes = (64 + 192 + 66) * 2 ** 20 + n_q * (2 * 16 + 4 + 4)
+            modes[name] = {'ms_per_update': ms, 'ms_per_training_step_amortised': ms / 16, 'candidate_cells': n_q, 'hbm_stream_bytes': stream_bytes,
+                           'stream_gbs': stream_bytes / (ms * 1e-3) / 1e9}
+        grid_upd = dict(modes, what='NGPGridSampler.update_density_grid_func: generate_grid_samples x2, density-only field (tcgen05), splat (atomicMax), EMA, bitfield + cascade pooling + mean')
+
     # ---- NeRF arm (BASELINE configs[2]: hierarchical 64 + 128, 800x800-shaped rays): fused tcgen05 NerfMLP path, device-resident rays
     nerf = None
     if not args.no_nerf:
@@ -419,6 +457,23 @@ def run_ours(args):
         s_mean = float(np.mean(samples))
         achieved = s_mean * BYTES_PER_SAMPLE / (f_ms * 1e-3) / 1e9
         cpu_rate, cores, kind, sample, _ = cpu_reference_rate(4096, reps=2) if world == 1 else (None, os.cpu_count(), 'reference', 'measured at N=1 only', None)
+        parity = None
+        if world == 1:   # the CPU arm just rendered 4096 rays of batch 0 with the reference arithmetic: compare this arm's render of the same rays (checker only)
+            rgb_cpu, alpha_cpu, ns_cpu = cpu_reference_rate.last
+            prn = NgpRenderer(field, samples_per_ray_budget=BUDGET, bg=(0., 0., 0.))
+            parity = {'rays': 4096, 'against': kind + ' CPU arm (oracle), fp32 march/composite + fp16 tcnn-shaped field'}
+            for path, fused_flag in (('chain', False), ('fused', True)):
+                prn.calls = 0                                   # same jitter stream as the CPU arm's call 0 (pcg32 seed 9121)
+                po, pd = dev_batches[0][0][:4096].contiguous(), dev_batches[0][1][:4096].contiguous()
+                if fused_flag:
+                    rgb_g, alpha_g, ns_g = prn.render_fused(po, pd, bf)
+                else:
+                    rgb_g, alpha_g, ns_g, _ = prn.render(po, pd, bf)
+                torch.cuda.synchronize()
+                err = np.abs(rgb_g.cpu().numpy() - rgb_cpu)
+                mse = float((err.astype(np.float64) ** 2).mean())
+                parity[path] = {'max_abs_rgb_err': float(err.max()), 'psnr_vs_ref_db': float(-10.0 * np.log10(max(mse, 1e-20))),
+                                'sample_counts_bit_exact': bool(np.array_equal(ns_g.cpu().numpy()[:, 0] if ns_g.dim() == 2 else ns_g.cpu().numpy(), ns_cpu))}
         chain = {'value': world * N_RAYS * K / (total_ms_max * 1e-3), 'unit': 'rays/s', 'ms_per_step': total_ms_max / K, 'gpu_launches_per_step': 5,
                  'what': '5 launches per batch on one stream (march count / scan / emit, field, composite), P batches in flight on P streams',
                  'roofline': {'kernel': 'xrb::ngp_field_tc_kernel<false>', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
@@ -445,7 +500,9 @@ def run_ours(args):
                              note='hash table (24.4 MB fp16) is L2-resident by design: the gather is served by L1/L2, so DRAM traffic (ncu, profiles/) is far below the algorithmic bytes'),
             'paths': {'chain': chain, 'fused': fused},
             'cpu_baseline': {'value': cpu_rate, 'unit': 'rays/s', 'cores': cores, 'kind': kind, 'sample': sample},
+            'parity': parity,
             'train': train,
+            'grid_update': grid_upd,
             'nerf': nerf,
             'mip': mip,
         }
@@ -462,6 +519,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-train', dest='no_train', action='store_true', help='skip the training arm')
     ap.add_argument('--no-nerf', dest='no_nerf', action='store_true', help='skip the vanilla-NeRF arm')
+    ap.add_argument('--no-grid', dest='no_grid', action='store_true', help='skip the occupancy-grid update arm')
     ap.add_argument('--no-mip', dest='no_mip', action='store_true', help='skip the Mip-NeRF arm')
     ap.add_argument('--path', default='auto', choices=['auto', 'chain', 'fused'], help='inference path of the headline/e2e numbers: 5-launch chain, single-launch fused kernel, or the faster of the two (both are always measured)')
     ap.add_argument('--pipeline', type=int, default=4, help='ray batches in flight (CUDA streams); 1 = strictly sequential steps')

@@ -1,0 +1,39 @@
+"""Developer probe: attribution of the NerfMLP v3 kernel time (XRB_NM_DBG bits: 1 no weight TMA, 2 no MMA, 4 no epilogue math) and v2 for comparison."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from xrnerf_b200 import registry as R, _C
+from xrnerf_b200.nerf_mlp import nerf_mlp_forward_tiles, pack_nerf_mlp_v2, pack_nerf_mlp_v3
+
+MLP = dict(type='NerfMLP', skips=[4], netdepth=8, netwidth=256, netchunk=1024 * 32, output_ch=5, use_viewdirs=True, embedder=dict(type='BaseEmbedder', i_embed=0, multires=10, multires_dirs=4))
+
+
+def timeit(fn, n=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+mlp = R.build_mlp(MLP).cuda()
+rows = 32768 * 64
+emb = torch.randn((rows, 90), device='cuda')
+flop = rows * 593408 * 2
+enc = torch.empty(_C.lib.xrb_nerf_enc_image_bytes(rows, 63), dtype=torch.uint8, device='cuda')
+_C.check(_C.lib.xrb_nerf_pack_embedded(_C.ptr(emb), rows, 63, 27, _C.ptr(enc), _C.stream()))
+raw = torch.empty((rows, 4), device='cuda')
+packs = {2: pack_nerf_mlp_v2(mlp), 3: pack_nerf_mlp_v3(mlp)}
+only = os.environ.get('PROBE_ONLY')
+for v in (3, 2):
+    for dbg in ([int(only)] if only else range(8)):
+        os.environ['XRB_NM_DBG'] = str(dbg)
+        image, bias = packs[v]
+        t = timeit(lambda: nerf_mlp_forward_tiles(image, bias, enc, rows, 63, 27, raw, version=v))
+        print(f'v{v} dbg={dbg} (tma {"off" if dbg & 1 else "on "} mma {"off" if dbg & 2 else "on "} epi {"off" if dbg & 4 else "on "}): {t:.3f} ms -> {flop / t / 1e9:.1f} TFLOP/s-equivalent', flush=True)
+    if only:
+        break

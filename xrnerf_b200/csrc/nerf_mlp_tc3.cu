@@ -19,6 +19,7 @@
 #include "tc.cuh"
 #include "common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace xrb {
 
@@ -36,7 +37,7 @@ struct N3Layer {
     int8_t wait_enc[N3_MAX_KB]; // issuer waits before K-block kb: 0 none, 1 = tile's first point block in AUX (+ second in H3, Mip), 2 = direction block, 3 = second point block in AUX
     int8_t reload[N3_MAX_KB];   // AUX is dead after K-block kb; the producer refills it with: 0 nothing, 1 = direction block, 2 = second point block, 3 = next tile's first point block
 };
-struct N3Plan { int n_layers, aux_blocks, bias_total, bias_h_off; N3Layer layer[N3_MAX_LAYERS]; };
+struct N3Plan { int n_layers, aux_blocks, bias_total, bias_h_off, dbg; N3Layer layer[N3_MAX_LAYERS]; };   // dbg (XRB_NM_DBG, attribution experiments): bit0 skip the weight TMA copies, bit1 skip the MMAs, bit2 skip the epilogue math
 
 __device__ __forceinline__ void n3_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory"); }
 
@@ -100,8 +101,8 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(N3Plan plan
                             for (int h = 0; h < L.n_halves; ++h, ++it) {
                                 const uint32_t slot = it % N3_RING, round = it / N3_RING;
                                 if (round > 0) tc::mbar_wait(b + B_EMPTY + slot, (round - 1) & 1);
-                                tc::mbar_expect_tx(b + B_FULL + slot, bytes);
-                                tc::tma_bulk_g2s(ring + (size_t)slot * N3_BLOCK, weight_image + off, bytes, b + B_FULL + slot);
+                                if (plan.dbg & 1) n3_arrive(b + B_FULL + slot);
+                                else { tc::mbar_expect_tx(b + B_FULL + slot, bytes); tc::tma_bulk_g2s(ring + (size_t)slot * N3_BLOCK, weight_image + off, bytes, b + B_FULL + slot); }
                                 off += bytes;
                             }
                             if (pending) {
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(N3Plan plan
                                 tc::mbar_wait(b + B_FULL + slot, round & 1);
                                 tc::tc_fence_after_sync();
                                 const uint32_t b0 = tc::smem_u32(ring + (size_t)slot * N3_BLOCK);
+                                if (!(plan.dbg & 2))
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) tc::mma_f16_ss(tmem_p + h * hw, tc::smem_desc_sw128(a0 + k * 32), tc::smem_desc_sw128(b0 + k * 32), idesc, (kb | k) ? 1u : 0u);
                                 tc::mma_commit(b + B_EMPTY + slot);
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(N3Plan plan
                 if (!last) {
                     const int cols = L.N >> 1, col0 = c * cols;
                     const __half2 zero2 = __float2half2_rn(0.f);
-                    for (int ck = 0; ck < cols / 32; ++ck) {
+                    for (int ck = 0; ck < ((plan.dbg & 4) ? 0 : cols / 32); ++ck) {
                         const int colb = col0 + ck * 32;
                         uint32_t r[32];
                         tc::tmem_ld32(taddr + colb, r);
@@ -283,6 +285,7 @@ int xrb_nerf_mlp_forward_v3(const void *weight_image, const float *bias, const v
     p.n_layers = nl;
     p.bias_total = boff + 257;                    // + Wa[256] + ba
     p.bias_h_off = (p.bias_total + 7) & ~7;       // fp16 copy of the per-layer biases follows the fp32 vector
+    p.dbg = getenv("XRB_NM_DBG") ? atoi(getenv("XRB_NM_DBG")) : 0;
     const size_t smem = 1024 + 2 * (size_t)N3_PIPE_A + 2 * (size_t)N3_RING * N3_BLOCK + 256 * sizeof(float) + 8 * (2 * B_PER_PIPE) + 16;
     static_assert(1024 + 2 * (size_t)N3_PIPE_A + 2 * (size_t)N3_RING * N3_BLOCK + 256 * sizeof(float) + 8 * (2 * B_PER_PIPE) + 16 <= 232448, "v3 shared memory budget");
     cudaFuncSetAttribute(nerf_mlp_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
