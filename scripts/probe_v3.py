@@ -29,7 +29,7 @@ _C.check(_C.lib.xrb_nerf_pack_embedded(_C.ptr(emb), rows, 63, 27, _C.ptr(enc), _
 raw = torch.empty((rows, 4), device='cuda')
 packs = {2: pack_nerf_mlp_v2(mlp), 3: pack_nerf_mlp_v3(mlp)}
 only = os.environ.get('PROBE_ONLY')
-for v in (3, 2):
+for v in ((3,) if os.environ.get('PROBE_V3_ONLY') else (3, 2)):
     for dbg in ([int(only)] if only else range(8)):
         os.environ['XRB_NM_DBG'] = str(dbg)
         image, bias = packs[v]

@@ -10,6 +10,8 @@
 //                TMA-loads the tile's encoding blocks;
 //   warps 18,19  MMA issuer of pipeline 0 / 1 (one lane): per K-block and output half 4 x tcgen05.mma (M=128, N=128|16, K=16) into the
 //                pipeline's 256 TMEM columns; everything a layer reads is complete before its epilogue rewrites H (no in-place race).
+// Synchronisation: compute -> issuer is a hardware named barrier (bar.arrive x256 / bar.sync x32); issuer -> compute is one mbarrier
+// (tcgen05.commit) polled by ONE thread per pipeline, fanned out by a named barrier; 6 polling threads per SM in total.
 //
 // Shared memory (227 KB): per pipeline H0-H3 (the 256-wide hidden state, 64 KB) + ONE 16 KB AUX block that holds, in turn, the point
 // encoding (layers 0 and 5), the view-direction encoding (views_linears.0) and then the next tile's point encoding; Mip-NeRF's second point
@@ -39,6 +41,7 @@ struct N3Layer {
 };
 struct N3Plan { int n_layers, aux_blocks, bias_total, bias_h_off, dbg; N3Layer layer[N3_MAX_LAYERS]; };   // dbg (XRB_NM_DBG, attribution experiments): bit0 skip the weight TMA copies, bit1 skip the MMAs, bit2 skip the epilogue math
 
+__device__ __forceinline__ void n3_bar_arrive(uint32_t id, uint32_t n_threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n_threads) : "memory"); }
 __device__ __forceinline__ void n3_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory"); }
 
 // barrier indices inside a pipeline's block of 16
@@ -58,7 +61,6 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(N3Plan plan
         for (int p = 0; p < 2; ++p) {
             uint64_t *b = bars + p * B_PER_PIPE;
             for (int s = 0; s < N3_RING; ++s) { tc::mbar_init(b + B_FULL + s, 1); tc::mbar_init(b + B_EMPTY + s, 1); }
-            tc::mbar_init(b + B_AREADY, 8);     // one elected arrival per compute warp of the pipeline (2 warpgroups)
             tc::mbar_init(b + B_ACC, 1);
             tc::mbar_init(b + B_E0, 1); tc::mbar_init(b + B_E1, 1); tc::mbar_init(b + B_E2, 1); tc::mbar_init(b + B_E3, 1);
             tc::mbar_init(b + B_AUXFREE, 1); tc::mbar_init(b + B_H3FREE, 1);
@@ -125,14 +127,16 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(N3Plan plan
                 }
             }
         } else {
-            // ===================================================== MMA issuer of pipeline p
-            if (lane == 0) {
-                uint32_t it = 0, a_phase = 0, tcount = 0;
-                const uint32_t tmem_p = tmem + (uint32_t)p * 256u;
-                for (int64_t tile = vcta; tile < n_tiles; tile += vstride, ++tcount) {
-                    for (int l = 0; l < plan.n_layers; ++l) {
-                        const N3Layer &L = plan.layer[l];
-                        tc::mbar_wait(b + B_AREADY, a_phase); a_phase ^= 1;     // the layer's input rows are in H, the previous accumulator is drained
+            // ===================================================== MMA issuer of pipeline p (the whole warp walks the loop: the layer hand-off from
+            // the 256 compute threads is a HARDWARE named barrier — bar.arrive x256 + bar.sync x32 — not a polled mbarrier; lane 0 issues)
+            uint32_t it = 0, tcount = 0;
+            const uint32_t tmem_p = tmem + (uint32_t)p * 256u;
+            for (int64_t tile = vcta; tile < n_tiles; tile += vstride, ++tcount) {
+                for (int l = 0; l < plan.n_layers; ++l) {
+                    const N3Layer &L = plan.layer[l];
+                    __syncwarp();
+                    tc::named_bar_sync(5 + p, 288);                             // the layer's input rows are in H, the previous accumulator is drained
+                    if (lane == 0) {
                         tc::tc_fence_after_sync();
                         const uint32_t hw = (uint32_t)(L.N / L.n_halves);
                         const uint32_t idesc = tc::idesc_f16_m128(hw);
@@ -178,16 +182,18 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(N3Plan plan
             const bool valid = i < n_rows;
             tc::tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) n3_arrive(b + B_AREADY);                // my warp's reads of the previous tile's accumulators are done
+            n3_bar_arrive(5 + p, 288);                             // my reads of the previous tile's accumulators are done (hardware barrier towards the issuer warp)
             float alpha_acc = 0.f;
             for (int l = 0; l < plan.n_layers; ++l) {
                 const N3Layer &L = plan.layer[l];
                 const bool last = l == plan.n_layers - 1;
-                if (!last || c == 0) {
-                    if (lane == 0) tc::mbar_wait(b + B_ACC, acc_phase);        // one poller per warp
-                    __syncwarp();
-                    tc::tc_fence_after_sync();
-                }
+                // ONE thread per pipeline polls the accumulator mbarrier (tcgen05.commit can only signal an mbarrier); the other 255 block in a hardware
+                // named barrier. 16 polling lanes executed 4.5 M try_waits per SM (ncu r01c: 47 % of all stall samples in the poll loop and its
+                // __syncwarp) and the polled mbarrier traffic delayed every other barrier operation: the bare synchronisation skeleton cost 2.07 of 3.98 ms.
+                if ((warp & 7) == 0 && lane == 0) tc::mbar_wait(b + B_ACC, acc_phase);
+                __syncwarp();
+                tc::named_bar_sync(3 + p, 256);
+                tc::tc_fence_after_sync();
                 acc_phase ^= 1;
                 if (!last) {
                     const int cols = L.N >> 1, col0 = c * cols;
@@ -209,7 +215,19 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(N3Plan plan
                                 h[e2] = __hadd2(__floats2half2_rn(__uint_as_float(r[8 * q + 2 * e2]), __uint_as_float(r[8 * q + 2 * e2 + 1])), b2[e2]);
                                 if (L.relu) h[e2] = __hmax2(h[e2], zero2);
                             }
-                            if (L.alpha_dot) {   // alpha_linear on the fp16 output of pts_linears.7: partial dot over my columns
+                            *reinterpret_cast<uint4 *>(dst + (((cb + (uint32_t)q) ^ r7) << 4)) = *reinterpret_cast<uint4 *>(h);
+                        }
+                    }
+                    if (L.alpha_dot) {   // alpha_linear on the fp16 output of pts_linears.7: partial dot over my columns, read back from my own row of H
+                        // (a warp-uniform branch taken once per tile; inside the chunk loop it was predicated code issued for every layer: 160 M FFMA + 60 M LDG slots)
+                        for (int ck = 0; ck < cols / 32; ++ck) {
+                            const int colb = col0 + ck * 32;
+                            const uint8_t *src = A + (size_t)(colb >> 6) * N3_BLOCK + row_off;
+                            const uint32_t cb = (uint32_t)(colb & 63) >> 3;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint4 hv = *reinterpret_cast<const uint4 *>(src + (((cb + (uint32_t)q) ^ r7) << 4));
+                                const __half2 *h = reinterpret_cast<const __half2 *>(&hv);
                                 const float4 w0 = __ldg(reinterpret_cast<const float4 *>(wa + colb + 8 * q)), w1 = __ldg(reinterpret_cast<const float4 *>(wa + colb + 8 * q + 4));
                                 float2 f;
                                 f = __half22float2(h[0]); alpha_acc = fmaf(f.x, w0.x, alpha_acc); alpha_acc = fmaf(f.y, w0.y, alpha_acc);
@@ -217,14 +235,13 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(N3Plan plan
                                 f = __half22float2(h[2]); alpha_acc = fmaf(f.x, w1.x, alpha_acc); alpha_acc = fmaf(f.y, w1.y, alpha_acc);
                                 f = __half22float2(h[3]); alpha_acc = fmaf(f.x, w1.z, alpha_acc); alpha_acc = fmaf(f.y, w1.w, alpha_acc);
                             }
-                            *reinterpret_cast<uint4 *>(dst + (((cb + (uint32_t)q) ^ r7) << 4)) = *reinterpret_cast<uint4 *>(h);
                         }
+                        if (c == 1) apart[row] = alpha_acc;
                     }
-                    if (L.alpha_dot && c == 1) apart[row] = alpha_acc;
                     tc::fence_proxy_async_smem();
                     tc::tc_fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) n3_arrive(b + B_AREADY);
+                    n3_bar_arrive(5 + p, 288);
                 } else {
                     if (c == 0) {
                         float o16[16];
