@@ -316,6 +316,21 @@ def run_ours(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
 
+    # ---- parity sample (N=1): this arm's render of the 4096 rays the CPU reference arm renders below, taken BEFORE the training arm updates the weights
+    parity_gpu = {}
+    if world == 1:
+        prn = NgpRenderer(field, samples_per_ray_budget=BUDGET, bg=(0., 0., 0.))
+        po, pd = dev_batches[0][0][:4096].contiguous(), dev_batches[0][1][:4096].contiguous()
+        for path in ('chain', 'fused'):
+            prn.calls = 0                                   # same jitter stream as the CPU arm's call 0 (pcg32 seed 9121)
+            if path == 'fused':
+                rgb_g, _, ns_g = prn.render_fused(po, pd, bf)
+            else:
+                rgb_g, _, ns_g, _ = prn.render(po, pd, bf)
+            torch.cuda.synchronize()
+            ns_np = ns_g.cpu().numpy()
+            parity_gpu[path] = (rgb_g.cpu().numpy().copy(), (ns_np[:, 0] if ns_np.ndim == 2 else ns_np).copy())
+
     # ---- training arm (fwd + bwd + all-reduce + Adam per step; device-resident batches; same rays, synthetic targets)
     train = None
     if not args.no_train:
@@ -460,20 +475,11 @@ def run_ours(args):
         parity = None
         if world == 1:   # the CPU arm just rendered 4096 rays of batch 0 with the reference arithmetic: compare this arm's render of the same rays (checker only)
             rgb_cpu, alpha_cpu, ns_cpu = cpu_reference_rate.last
-            prn = NgpRenderer(field, samples_per_ray_budget=BUDGET, bg=(0., 0., 0.))
             parity = {'rays': 4096, 'against': kind + ' CPU arm (oracle), fp32 march/composite + fp16 tcnn-shaped field'}
-            for path, fused_flag in (('chain', False), ('fused', True)):
-                prn.calls = 0                                   # same jitter stream as the CPU arm's call 0 (pcg32 seed 9121)
-                po, pd = dev_batches[0][0][:4096].contiguous(), dev_batches[0][1][:4096].contiguous()
-                if fused_flag:
-                    rgb_g, alpha_g, ns_g = prn.render_fused(po, pd, bf)
-                else:
-                    rgb_g, alpha_g, ns_g, _ = prn.render(po, pd, bf)
-                torch.cuda.synchronize()
-                err = np.abs(rgb_g.cpu().numpy() - rgb_cpu)
+            for path, (rgb_g, ns_g) in parity_gpu.items():
+                err = np.abs(rgb_g - rgb_cpu)
                 mse = float((err.astype(np.float64) ** 2).mean())
-                parity[path] = {'max_abs_rgb_err': float(err.max()), 'psnr_vs_ref_db': float(-10.0 * np.log10(max(mse, 1e-20))),
-                                'sample_counts_bit_exact': bool(np.array_equal(ns_g.cpu().numpy()[:, 0] if ns_g.dim() == 2 else ns_g.cpu().numpy(), ns_cpu))}
+                parity[path] = {'max_abs_rgb_err': float(err.max()), 'psnr_vs_ref_db': float(-10.0 * np.log10(max(mse, 1e-20))), 'sample_counts_bit_exact': bool(np.array_equal(ns_g, ns_cpu))}
         chain = {'value': world * N_RAYS * K / (total_ms_max * 1e-3), 'unit': 'rays/s', 'ms_per_step': total_ms_max / K, 'gpu_launches_per_step': 5,
                  'what': '5 launches per batch on one stream (march count / scan / emit, field, composite), P batches in flight on P streams',
                  'roofline': {'kernel': 'xrb::ngp_field_tc_kernel<false>', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,

@@ -35,6 +35,30 @@ __global__ void lat_kernel(long long *out) {
         t0 = clock64();
         for (int q = 0; q < 8; ++q) for (int k = 0; k < 4; ++k) tc::mma_f16_ss(tmem, tc::smem_desc_sw128(a0 + k * 32), tc::smem_desc_sw128(b0 + k * 32), tc::idesc_f16_m128(128), 1);
         ti = clock64(); tc::mma_commit(bar); tc::mbar_wait(bar, ph); ph ^= 1; t1 = clock64(); out[10] = ti - t0; out[11] = t1 - t0;
+        // (i) ISSUE cost of tcgen05.commit (no wait), then 8 commits back to back on 8 barriers, then their completion
+        {
+            uint64_t *bx = (uint64_t *)(base + 65536 + 256);
+            for (int q = 0; q < 8; ++q) tc::mbar_init(bx + q, 1);
+            tc::fence_mbar_init();
+            long long c0 = clock64(); tc::mma_commit(bx); long long c1 = clock64(); out[21] = c1 - c0;
+            tc::mbar_wait(bx, 0);
+            c0 = clock64();
+            for (int q = 1; q < 8; ++q) tc::mma_commit(bx + q);
+            c1 = clock64(); out[22] = c1 - c0;
+            for (int q = 1; q < 8; ++q) tc::mbar_wait(bx + q, 0);
+            out[23] = clock64() - c0;
+            // 4 MMAs + commit, 8 times back to back (issue time), then completion
+            for (int q = 0; q < 8; ++q) tc::mbar_init(bx + q, 1);
+            tc::fence_mbar_init();
+            c0 = clock64();
+            for (int q = 0; q < 8; ++q) {
+                for (int k = 0; k < 4; ++k) tc::mma_f16_ss(tmem, tc::smem_desc_sw128(a0 + k * 32), tc::smem_desc_sw128(b0 + k * 32), tc::idesc_f16_m128(128), 1);
+                tc::mma_commit(bx + q);
+            }
+            c1 = clock64(); out[24] = c1 - c0;
+            for (int q = 0; q < 8; ++q) tc::mbar_wait(bx + q, 0);
+            out[25] = clock64() - c0;
+        }
         // (e) fence.proxy.async cost, tcgen05 fences
         t0 = clock64(); tc::fence_proxy_async_smem(); t1 = clock64(); out[12] = t1 - t0;
         t0 = clock64(); tc::tc_fence_before_sync(); tc::tc_fence_after_sync(); t1 = clock64(); out[13] = t1 - t0;
@@ -64,10 +88,10 @@ int main() {
     long long *d; cudaMalloc(&d, 1 << 20); cudaMemset(d, 0, 1 << 20);
     cudaFuncSetAttribute(lat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100000);
     lat_kernel<<<1, 192, 100000>>>(d); cudaError_t e = cudaDeviceSynchronize();
-    long long h[32]; cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    long long h[40]; cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
     printf("err=%s\n", cudaGetErrorString(e));
     const char *names[] = {"commit(empty)->wait #1", "commit(empty)->wait #2", "issue 4xMMA N256 (a)", "4xMMA N256 + commit -> done (a)", "issue (b)", "done (b)", "issue (c)", "done (c)", "issue 16xMMA N256", "16xMMA N256 done",
-                           "issue 32xMMA N128", "32xMMA N128 done", "fence.proxy.async", "tcgen05 fences", "mbarrier arrive->wait hop", "tmem_ld32+wait", "(r0)", "TMA 16KB #1", "TMA 16KB #2", "TMA 16KB #3", "TMA 2x16KB"};
-    for (int i = 0; i < 21; ++i) printf("%-34s %lld cycles\n", names[i], h[i]);
+                           "issue 32xMMA N128", "32xMMA N128 done", "fence.proxy.async", "tcgen05 fences", "mbarrier arrive->wait hop", "tmem_ld32+wait", "(r0)", "TMA 16KB #1", "TMA 16KB #2", "TMA 16KB #3", "TMA 2x16KB", "issue 1 commit", "issue 7 commits", "7 commits landed", "issue 8x(4 MMA N128 + commit)", "8x(4 MMA N128 + commit) landed"};
+    for (int i = 0; i < 26; ++i) printf("%-34s %lld cycles\n", names[i], h[i]);
     return 0;
 }
