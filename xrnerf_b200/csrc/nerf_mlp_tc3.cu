@@ -130,53 +130,63 @@ __device__ __forceinline__ void n3_produce_tile(std::integer_sequence<int, LS...
 }
 
 // ---------------------------------------------------------------------------------------------------- MMA issuer (whole warp walks, lane 0 issues)
+// The issuer warp runs CONVERGED (all 32 lanes walk the schedule and wait on the barriers; one elected lane executes tcgen05.mma / commit): every
+// operand is then provably warp-uniform and lives in uniform registers. Issued from `if (lane == 0)` code each MMA cost a 5 x R2UR.BROADCAST waterfall
+// loop (~65 cycles per MMA, as long as an N=128 MMA executes), so the single issuing thread, not the tensor pipe, set the pace (timeline r01c).
+__device__ __forceinline__ bool n3_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 template <bool MIP, int LX>
-__device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uint32_t tcount, int lane) {
+__device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uint32_t tcount) {
     constexpr N3L L = n3_layer<MIP>(LX);
     constexpr uint32_t hw = (uint32_t)(L.N / L.n_halves);
     constexpr uint32_t idesc = tc::idesc_f16_m128(hw);
     constexpr uint32_t SRC = n3_pack(L.src, 3), WE = n3_pack(L.wait_enc, 2), RL = n3_pack(L.reload, 2);
-    __syncwarp();
     tc::named_bar_sync(5 + c.p, 288);                             // the layer's input rows are in H, the previous accumulator is drained (hardware barrier)
     const bool tr = (c.dbg & 16) && blockIdx.x == 0 && c.p == 0 && tcount == 2;
-    if (lane == 0) {
-        if (tr) n3_trace_buf[0][LX] = clock64();
-        tc::tc_fence_after_sync();
-        const uint32_t a_lo = n3_desc_lo(tc::smem_u32(c.A)), b_lo = n3_desc_lo(tc::smem_u32(c.ring));
+    if (tr && n3_elect_one()) n3_trace_buf[0][LX] = clock64();
+    tc::tc_fence_after_sync();
+    const uint32_t a_lo = n3_desc_lo(tc::smem_u32(c.A)), b_lo = n3_desc_lo(tc::smem_u32(c.ring));
 #pragma unroll 1
-        for (int kb = 0; kb < L.n_kb; ++kb) {
-            const uint32_t we = (WE >> (2 * kb)) & 3u;
-            if (we) {
-                if (we == 1) { tc::mbar_wait(c.b + B_E0, tcount & 1); if (MIP) tc::mbar_wait(c.b + B_E3, tcount & 1); }
-                else tc::mbar_wait(c.b + (we == 2 ? B_E1 : B_E2), tcount & 1);
-                tc::tc_fence_after_sync();
-            }
-            const uint32_t a0 = a_lo + ((SRC >> (3 * kb)) & 7u) * (N3_BLOCK >> 4);
-#pragma unroll 1
-            for (int h = 0; h < L.n_halves; ++h, ++it) {
-                const uint32_t slot = it % N3_RING, round = it / N3_RING;
-                if (c.dbg & 8) continue;
-                tc::mbar_wait(c.b + B_FULL + slot, round & 1);
-                tc::tc_fence_after_sync();
-                const uint32_t b0 = b_lo + slot * (N3_BLOCK >> 4);
+    for (int kb = 0; kb < L.n_kb; ++kb) {
+        const uint32_t we = (WE >> (2 * kb)) & 3u;
+        if (we) {
+            if (we == 1) { tc::mbar_wait(c.b + B_E0, tcount & 1); if (MIP) tc::mbar_wait(c.b + B_E3, tcount & 1); }
+            else tc::mbar_wait(c.b + (we == 2 ? B_E1 : B_E2), tcount & 1);
+            tc::tc_fence_after_sync();
+        }
+        const uint32_t a0 = a_lo + ((SRC >> (3 * kb)) & 7u) * (N3_BLOCK >> 4);
+#pragma unroll
+        for (int h = 0; h < L.n_halves; ++h, ++it) {
+            const uint32_t slot = it % N3_RING, round = it / N3_RING;
+            if (c.dbg & 8) continue;
+            tc::mbar_wait(c.b + B_FULL + slot, round & 1);
+            tc::tc_fence_after_sync();
+            const uint32_t b0 = b_lo + slot * (N3_BLOCK >> 4);
+            if (n3_elect_one()) {
                 if (!(c.dbg & 2)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) tc::mma_f16_ss(c.tmem_p + h * hw, n3_desc(a0 + 2 * k), n3_desc(b0 + 2 * k), idesc, (kb | k) ? 1u : 0u);   // +32 bytes per K step of 16
                 }
                 tc::mma_commit(c.b + B_EMPTY + slot);
             }
-            if ((RL >> (2 * kb)) & 3u) tc::mma_commit(c.b + B_AUXFREE);       // every MMA that reads AUX's current content has been issued
+            __syncwarp();
         }
+        if (((RL >> (2 * kb)) & 3u) && n3_elect_one()) tc::mma_commit(c.b + B_AUXFREE);       // every MMA that reads AUX's current content has been issued
+        __syncwarp();
+    }
+    if (n3_elect_one()) {
         if (L.commit_h3) tc::mma_commit(c.b + B_H3FREE);
         tc::mma_commit(c.b + B_ACC);                                  // accumulator of layer LX complete, H/AUX reads of the layer done
         if (tr) n3_trace_buf[1][LX] = clock64();
-    } else {
-        it += (uint32_t)(L.n_kb * L.n_halves);
     }
+    __syncwarp();
 }
 template <bool MIP, int... LS>
-__device__ __forceinline__ void n3_issue_tile(std::integer_sequence<int, LS...>, const N3Ctx &c, uint32_t &it, uint32_t tcount, int lane) {
-    (n3_issue_layer<MIP, LS>(c, it, tcount, lane), ...);
+__device__ __forceinline__ void n3_issue_tile(std::integer_sequence<int, LS...>, const N3Ctx &c, uint32_t &it, uint32_t tcount) {
+    (n3_issue_layer<MIP, LS>(c, it, tcount), ...);
 }
 
 // ---------------------------------------------------------------------------------------------------- compute warpgroups
@@ -275,7 +285,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, co
     float *alpha_part = (float *)(ring_base + 2 * N3_RING * N3_BLOCK);          // [2][128]
     uint64_t *bars = (uint64_t *)(alpha_part + 256);
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * B_PER_PIPE);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform by construction (uniform registers)
     using Layers = std::make_integer_sequence<int, N3_LAYERS>;
 
     if (threadIdx.x == 0) {
@@ -292,7 +302,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, co
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int64_t n_tiles = (n_rows + 127) / 128;
     constexpr uint32_t enc_tile_bytes = (uint32_t)((MIP ? 2 : 1) + 1) * N3_BLOCK;
 
@@ -305,7 +315,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, co
     if (warp >= 18) {
         // ===================================================== MMA issuer of pipeline p
         uint32_t it = 0, tcount = 0;
-        for (int64_t tile = vcta; tile < n_tiles; tile += vstride, ++tcount) n3_issue_tile<MIP>(Layers{}, c, it, tcount, lane);
+        for (int64_t tile = vcta; tile < n_tiles; tile += vstride, ++tcount) n3_issue_tile<MIP>(Layers{}, c, it, tcount);
     } else if (warp >= 16) {
         // ===================================================== producer of pipeline p
         if (lane == 0) {
