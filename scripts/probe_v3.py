@@ -30,7 +30,7 @@ raw = torch.empty((rows, 4), device='cuda')
 packs = {2: pack_nerf_mlp_v2(mlp), 3: pack_nerf_mlp_v3(mlp)}
 only = os.environ.get('PROBE_ONLY')
 for v in ((3,) if os.environ.get('PROBE_V3_ONLY') else (3, 2)):
-    for dbg in ([int(only)] if only else (list(range(8)) + [15])):
+    for dbg in ([int(only)] if only else [0, 2, 4]):
         os.environ['XRB_NM_DBG'] = str(dbg)
         image, bias = packs[v]
         t = timeit(lambda: nerf_mlp_forward_tiles(image, bias, enc, rows, 63, 27, raw, version=v))
@@ -38,16 +38,23 @@ for v in ((3,) if os.environ.get('PROBE_V3_ONLY') else (3, 2)):
     if only:
         break
 
+for stg in (0, 3000):
+    os.environ['XRB_NM_DBG'] = '0'; os.environ['XRB_N3_STAGGER'] = str(stg)
+    image, bias = packs[3]
+    t = timeit(lambda: nerf_mlp_forward_tiles(image, bias, enc, rows, 63, 27, raw, version=3), n=10)
+    print(f'v3 stagger={stg}: {t:.3f} ms -> {flop / t / 1e9:.1f} TFLOP/s-equivalent', flush=True)
+os.environ['XRB_N3_STAGGER'] = '3000'
 # ---- timeline of one tile (dbg bit4): issuer / poller / compute time stamps per layer, in cycles relative to the layer-0 issuer start
 import ctypes, numpy as np
 _C.lib.xrb_internal_n3_trace.argtypes = [ctypes.c_void_p]
-for dbg in (16, 16 + 7, 16 + 15):
+for dbg, stg in ((16, 0), (16, 3000)):
+    os.environ['XRB_N3_STAGGER'] = str(stg)
     os.environ['XRB_NM_DBG'] = str(dbg)
     image, bias = packs[3]
     nerf_mlp_forward_tiles(image, bias, enc, rows, 63, 27, raw, version=3); torch.cuda.synchronize()
     buf = np.zeros((8, 16), np.int64)
     _C.lib.xrb_internal_n3_trace(buf.ctypes.data)
     t0 = buf[0, 0]
-    print(f'--- timeline dbg={dbg}: per layer [issuer start, issuer committed, poller woke, warp0 released, warp7 released, warp0 epi done, warp7 epi done] (cycles since layer-0 start)')
+    print(f'--- timeline dbg={dbg}: per layer [P0 issuer start, P0 committed, P0 poller woke, P0 released, P1 issuer start, P0 epi done (w0), P0 epi done (w7), P1 committed] (cycles since layer-0 start)')
     for l in range(11):
-        print(f'  L{l:2d} ' + ' '.join(f'{int(buf[e, l] - t0):7d}' for e in range(7)))
+        print(f'  L{l:2d} ' + ' '.join(f'{int(buf[e, l] - t0):7d}' for e in range(8)))

@@ -145,8 +145,8 @@ __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uin
     constexpr uint32_t idesc = tc::idesc_f16_m128(hw);
     constexpr uint32_t SRC = n3_pack(L.src, 3), WE = n3_pack(L.wait_enc, 2), RL = n3_pack(L.reload, 2);
     tc::named_bar_sync(5 + c.p, 288);                             // the layer's input rows are in H, the previous accumulator is drained (hardware barrier)
-    const bool tr = (c.dbg & 16) && blockIdx.x == 0 && c.p == 0 && tcount == 2;
-    if (tr && n3_elect_one()) n3_trace_buf[0][LX] = clock64();
+    const bool tr = (c.dbg & 16) && blockIdx.x == 0 && tcount == 2;     // both pipelines' issuers are traced: events 0/1 (pipeline 0), 4/7 (pipeline 1)
+    if (tr && n3_elect_one()) n3_trace_buf[c.p ? 4 : 0][LX] = clock64();
     tc::tc_fence_after_sync();
     const uint32_t a_lo = n3_desc_lo(tc::smem_u32(c.A)), b_lo = n3_desc_lo(tc::smem_u32(c.ring));
 #pragma unroll 1
@@ -180,7 +180,7 @@ __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uin
     if (n3_elect_one()) {
         if (L.commit_h3) tc::mma_commit(c.b + B_H3FREE);
         tc::mma_commit(c.b + B_ACC);                                  // accumulator of layer LX complete, H/AUX reads of the layer done
-        if (tr) n3_trace_buf[1][LX] = clock64();
+        if (tr) n3_trace_buf[c.p ? 7 : 1][LX] = clock64();
     }
     __syncwarp();
 }
@@ -203,7 +203,7 @@ __device__ __forceinline__ void n3_epilogue_layer(const N3Ctx &c, N3Comp &s) {
     if ((s.warp & 7) == 0 && s.lane == 0) { tc::mbar_wait(c.b + B_ACC, s.acc_phase); if (s.tr) n3_trace_buf[2][LX] = clock64(); }
     __syncwarp();
     tc::named_bar_sync(3 + c.p, 256);
-    if (s.tr && (threadIdx.x == 1 || threadIdx.x == 224)) n3_trace_buf[threadIdx.x == 1 ? 3 : 4][LX] = clock64();
+    if (s.tr && threadIdx.x == 1) n3_trace_buf[3][LX] = clock64();
     tc::tc_fence_after_sync();
     s.acc_phase ^= 1;
     if (!last) {
@@ -277,7 +277,7 @@ __device__ __forceinline__ void n3_epilogue_tile(std::integer_sequence<int, LS..
 }
 
 template <bool MIP>
-__global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, const uint8_t *__restrict__ weight_image, const float *__restrict__ bias_g, const uint8_t *__restrict__ enc_image,
+__global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, int stagger, const uint8_t *__restrict__ weight_image, const float *__restrict__ bias_g, const uint8_t *__restrict__ enc_image,
                                                                       int64_t n_rows, float *__restrict__ raw) {
     extern __shared__ uint8_t dyn_smem[];
     uint8_t *base = (uint8_t *)(((uintptr_t)dyn_smem + 1023) & ~(uintptr_t)1023);
@@ -314,6 +314,10 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, co
 
     if (warp >= 18) {
         // ===================================================== MMA issuer of pipeline p
+        // Both pipelines start together and would stay IN PHASE (sharing the tensor pipe half/half during their MMA phases and leaving it idle during
+        // both epilogues: the r01c timeline shows 4.1 K-cycle MMA phases = 2 x 2048). The phase offset between them is neutrally stable, so pipeline 1
+        // simply starts half a layer period late and the two alternate: one drains its accumulators while the other one's MMAs run.
+        if (c.p == 1) { const long long t0 = clock64(); while (clock64() - t0 < (long long)stagger) {} }
         uint32_t it = 0, tcount = 0;
         for (int64_t tile = vcta; tile < n_tiles; tile += vstride, ++tcount) n3_issue_tile<MIP>(Layers{}, c, it, tcount);
     } else if (warp >= 16) {
@@ -380,6 +384,7 @@ int xrb_nerf_mlp_forward_v3(const void *weight_image, const float *bias, const v
                 "nerf_mlp_forward_v3: images / bias / raw must be 16-byte aligned");
     const bool mip = input_ch > 64;
     const int dbg = getenv("XRB_NM_DBG") ? atoi(getenv("XRB_NM_DBG")) : 0;   // attribution experiments: bit0 no weight TMA, bit1 no MMAs, bit2 no epilogue math, bit3 (with 0|1) no weight-ring handshake, bit4 timeline
+    const int stagger = getenv("XRB_N3_STAGGER") ? atoi(getenv("XRB_N3_STAGGER")) : 3000;   // cycles by which pipeline 1 trails pipeline 0 (see the kernel)
     constexpr size_t smem = 1024 + 2 * (size_t)N3_PIPE_A + 2 * (size_t)N3_RING * N3_BLOCK + 256 * sizeof(float) + 8 * (2 * B_PER_PIPE) + 16;
     static_assert(smem <= 232448, "v3 shared memory budget");
     int dev = 0, sms = NUM_SMS; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -387,10 +392,10 @@ int xrb_nerf_mlp_forward_v3(const void *weight_image, const float *bias, const v
     const int grid = (int)(pairs < sms ? pairs : sms);
     if (mip) {
         cudaFuncSetAttribute(nerf_mlp_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        nerf_mlp_tc3_kernel<true><<<grid, N3_THREADS, smem, (cudaStream_t)stream>>>(dbg, (const uint8_t *)weight_image, bias, (const uint8_t *)enc_image, n_rows, raw);
+        nerf_mlp_tc3_kernel<true><<<grid, N3_THREADS, smem, (cudaStream_t)stream>>>(dbg, stagger, (const uint8_t *)weight_image, bias, (const uint8_t *)enc_image, n_rows, raw);
     } else {
         cudaFuncSetAttribute(nerf_mlp_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        nerf_mlp_tc3_kernel<false><<<grid, N3_THREADS, smem, (cudaStream_t)stream>>>(dbg, (const uint8_t *)weight_image, bias, (const uint8_t *)enc_image, n_rows, raw);
+        nerf_mlp_tc3_kernel<false><<<grid, N3_THREADS, smem, (cudaStream_t)stream>>>(dbg, stagger, (const uint8_t *)weight_image, bias, (const uint8_t *)enc_image, n_rows, raw);
     }
     return check_launch("nerf_mlp_forward_v3");
 }

@@ -52,7 +52,7 @@ class NerfMLP(BaseMLP):
 
     def _packed(self):
         import os
-        self.kernel_version = int(os.environ.get('XRB_NERF_MLP_V', '2'))
+        self.kernel_version = int(os.environ.get('XRB_NERF_MLP_V', '3'))
         ver = tuple(p._version for p in self.parameters()) + (self.pts_linears[0].weight.device, self.kernel_version)
         if getattr(self, '_pack_ver', None) != ver:
             from ..nerf_mlp import pack_nerf_mlp, pack_nerf_mlp_v2, pack_nerf_mlp_v3
