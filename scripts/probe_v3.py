@@ -30,7 +30,7 @@ raw = torch.empty((rows, 4), device='cuda')
 packs = {2: pack_nerf_mlp_v2(mlp), 3: pack_nerf_mlp_v3(mlp)}
 only = os.environ.get('PROBE_ONLY')
 for v in ((3,) if os.environ.get('PROBE_V3_ONLY') else (3, 2)):
-    for dbg in ([int(only)] if only else [0, 2, 4]):
+    for dbg in ([int(only)] if only else [0]):
         os.environ['XRB_NM_DBG'] = str(dbg)
         image, bias = packs[v]
         t = timeit(lambda: nerf_mlp_forward_tiles(image, bias, enc, rows, 63, 27, raw, version=v))
@@ -38,7 +38,7 @@ for v in ((3,) if os.environ.get('PROBE_V3_ONLY') else (3, 2)):
     if only:
         break
 
-for stg in (0, 3000):
+for stg in ():
     os.environ['XRB_NM_DBG'] = '0'; os.environ['XRB_N3_STAGGER'] = str(stg)
     image, bias = packs[3]
     t = timeit(lambda: nerf_mlp_forward_tiles(image, bias, enc, rows, 63, 27, raw, version=3), n=10)
@@ -47,7 +47,7 @@ os.environ['XRB_N3_STAGGER'] = '3000'
 # ---- timeline of one tile (dbg bit4): issuer / poller / compute time stamps per layer, in cycles relative to the layer-0 issuer start
 import ctypes, numpy as np
 _C.lib.xrb_internal_n3_trace.argtypes = [ctypes.c_void_p]
-for dbg, stg in ((16, 0), (16, 3000)):
+for dbg, stg in ((16, 0),):
     os.environ['XRB_N3_STAGGER'] = str(stg)
     os.environ['XRB_NM_DBG'] = str(dbg)
     image, bias = packs[3]

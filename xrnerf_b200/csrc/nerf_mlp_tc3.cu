@@ -76,6 +76,7 @@ __host__ __device__ constexpr N3L n3_layer(int l) {
 // single thread) and index the schedule with shifts instead of loads
 __host__ __device__ constexpr uint32_t n3_pack(const int *v, int bits) { uint32_t r = 0; for (int k = 0; k < N3_MAX_KB; ++k) r |= (uint32_t)v[k] << (bits * k); return r; }
 __device__ __forceinline__ uint64_t n3_desc(uint32_t lo) { return ((uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32) | (uint64_t)lo; }   // tc::smem_desc_sw128 split: hi word constant
+__device__ __forceinline__ uint64_t n3_desc64(uint32_t lo) { return ((uint64_t)((512u >> 4) | (1u << 14) | (4u << 29)) << 32) | (uint64_t)lo; }   // K-major SWIZZLE_64B: 8-row atoms of 64-byte rows, 512 B apart
 __device__ __forceinline__ uint32_t n3_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
 
 __device__ long long n3_trace_buf[8][16];   // developer timeline (dbg bit4): [event][layer] clock64 of block 0 / pipeline 0 / its 3rd tile
@@ -86,7 +87,7 @@ __device__ __forceinline__ void n3_arrive(uint64_t *bar) { asm volatile("mbarrie
 enum { B_FULL = 0, B_EMPTY = 2, B_ACC = 5, B_E0 = 6, B_E1 = 7, B_E2 = 8, B_E3 = 9, B_AUXFREE = 10, B_H3FREE = 11, B_PER_PIPE = 16 };
 
 struct N3Ctx {            // per-role constants of one pipeline
-    uint64_t *b; uint8_t *A; uint8_t *ring; int p, dbg; uint32_t tmem_p;
+    uint64_t *b; uint8_t *A; uint8_t *ring; int p, dbg; uint32_t tmem_p; volatile uint32_t *busy;   // busy[p]: issuer p is inside a layer's issue phase
 };
 
 // ---------------------------------------------------------------------------------------------------- producer (one lane)
@@ -141,11 +142,23 @@ __device__ __forceinline__ bool n3_elect_one() {
 template <bool MIP, int LX>
 __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uint32_t tcount) {
     constexpr N3L L = n3_layer<MIP>(LX);
-    constexpr uint32_t hw = (uint32_t)(L.N / L.n_halves);
-    constexpr uint32_t idesc = tc::idesc_f16_m128(hw);
+    constexpr uint32_t idesc = tc::idesc_f16_m128((uint32_t)L.N);
     constexpr uint32_t SRC = n3_pack(L.src, 3), WE = n3_pack(L.wait_enc, 2), RL = n3_pack(L.reload, 2);
     tc::named_bar_sync(5 + c.p, 288);                             // the layer's input rows are in H, the previous accumulator is drained (hardware barrier)
     const bool tr = (c.dbg & 16) && blockIdx.x == 0 && tcount == 2;     // both pipelines' issuers are traced: events 0/1 (pipeline 0), 4/7 (pipeline 1)
+    // Tensor-pipe turn taking. Left alone the two pipelines LOCK IN PHASE (timeline r01c: both issuers start every layer within ~20 cycles of each
+    // other, even when pipeline 1 is started 3000 cycles late): their MMA phases then share the pipe half/half (4.1 K cycles = 2 x 2048) and it idles
+    // during both epilogues. So an issuer does not start a layer while the other one is issuing; pipeline 1 looks a little later than pipeline 0
+    // raises its flag, which breaks the tie. The flag drops when the layer's last MMA has been ISSUED (the pipe still holds ~2 slabs of queued work,
+    // so the hand-over leaves no gap). Neither side ever waits while the other cannot make progress: a waiter only waits on an issuing pipeline.
+    if (c.dbg & 32) {   // measured: 2.68 ms with turn taking vs 2.35 ms without — the MMA phase is 4.1 K cycles even ALONE on the pipe (shared-memory bytes), so it stays an experiment
+        if (c.p == 1) __nanosleep(64);
+        else if (n3_elect_one()) c.busy[0] = 1;
+        __syncwarp();
+        while (c.busy[c.p ^ 1]) {}
+        if (c.p == 1 && n3_elect_one()) c.busy[1] = 1;
+        __syncwarp();
+    }
     if (tr && n3_elect_one()) n3_trace_buf[c.p ? 4 : 0][LX] = clock64();
     tc::tc_fence_after_sync();
     const uint32_t a_lo = n3_desc_lo(tc::smem_u32(c.A)), b_lo = n3_desc_lo(tc::smem_u32(c.ring));
@@ -167,8 +180,16 @@ __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uin
             const uint32_t b0 = b_lo + slot * (N3_BLOCK >> 4);
             if (n3_elect_one()) {
                 if (!(c.dbg & 2)) {
+                    if (L.n_halves == 2) {
+                        // N=256 layers: the slab is a K-HALF of the K-block, [256 x 32] fp16 in the 64-byte-swizzle layout: two N=256 MMAs per slab read every
+                        // A element once (N=128 halves read A twice: 448 KB of shared-memory traffic per tile-layer against a 128 B/clk port = the 3.5 K-cycle
+                        // tile-layers of the r01c timeline; this layout needs 384 KB)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) tc::mma_f16_ss(c.tmem_p + h * hw, n3_desc(a0 + 2 * k), n3_desc(b0 + 2 * k), idesc, (kb | k) ? 1u : 0u);   // +32 bytes per K step of 16
+                        for (int k = 0; k < 2; ++k) tc::mma_f16_ss(c.tmem_p, n3_desc(a0 + 2 * (2 * h + k)), n3_desc64(b0 + 2 * k), idesc, (kb | h | k) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) tc::mma_f16_ss(c.tmem_p, n3_desc(a0 + 2 * k), n3_desc(b0 + 2 * k), idesc, (kb | k) ? 1u : 0u);   // +32 bytes per K step of 16
+                    }
                 }
                 tc::mma_commit(c.b + B_EMPTY + slot);
             }
@@ -180,6 +201,7 @@ __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uin
     if (n3_elect_one()) {
         if (L.commit_h3) tc::mma_commit(c.b + B_H3FREE);
         tc::mma_commit(c.b + B_ACC);                                  // accumulator of layer LX complete, H/AUX reads of the layer done
+        c.busy[c.p] = 0;
         if (tr) n3_trace_buf[c.p ? 7 : 1][LX] = clock64();
     }
     __syncwarp();
@@ -285,10 +307,12 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
     float *alpha_part = (float *)(ring_base + 2 * N3_RING * N3_BLOCK);          // [2][128]
     uint64_t *bars = (uint64_t *)(alpha_part + 256);
     uint32_t *tmem_slot = (uint32_t *)(bars + 2 * B_PER_PIPE);
+    volatile uint32_t *busy = tmem_slot + 1;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform by construction (uniform registers)
     using Layers = std::make_integer_sequence<int, N3_LAYERS>;
 
     if (threadIdx.x == 0) {
+        busy[0] = 0; busy[1] = 0;
         for (int p = 0; p < 2; ++p) {
             uint64_t *b = bars + p * B_PER_PIPE;
             for (int s = 0; s < N3_RING; ++s) { tc::mbar_init(b + B_FULL + s, 1); tc::mbar_init(b + B_EMPTY + s, 1); }
@@ -309,7 +333,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
     N3Ctx c;
     c.p = warp >= 16 ? (warp & 1) : (warp >> 3);                 // warps 16,18 / 0-7 -> pipeline 0; 17,19 / 8-15 -> pipeline 1
     c.b = bars + c.p * B_PER_PIPE; c.A = base + (size_t)c.p * N3_PIPE_A; c.ring = ring_base + (size_t)c.p * N3_RING * N3_BLOCK; c.dbg = dbg;
-    c.tmem_p = tmem + (uint32_t)c.p * 256u;
+    c.tmem_p = tmem + (uint32_t)c.p * 256u; c.busy = busy;
     const int64_t vcta = (int64_t)blockIdx.x * 2 + c.p, vstride = (int64_t)gridDim.x * 2;
 
     if (warp >= 18) {
@@ -383,8 +407,8 @@ int xrb_nerf_mlp_forward_v3(const void *weight_image, const float *bias, const v
     XRB_REQUIRE(((uintptr_t)weight_image & 15) == 0 && ((uintptr_t)raw & 15) == 0 && ((uintptr_t)enc_image & 15) == 0 && ((uintptr_t)bias & 15) == 0,
                 "nerf_mlp_forward_v3: images / bias / raw must be 16-byte aligned");
     const bool mip = input_ch > 64;
-    const int dbg = getenv("XRB_NM_DBG") ? atoi(getenv("XRB_NM_DBG")) : 0;   // attribution experiments: bit0 no weight TMA, bit1 no MMAs, bit2 no epilogue math, bit3 (with 0|1) no weight-ring handshake, bit4 timeline
-    const int stagger = getenv("XRB_N3_STAGGER") ? atoi(getenv("XRB_N3_STAGGER")) : 3000;   // cycles by which pipeline 1 trails pipeline 0 (see the kernel)
+    const int dbg = getenv("XRB_NM_DBG") ? atoi(getenv("XRB_NM_DBG")) : 0;   // attribution experiments: bit0 no weight TMA, bit1 no MMAs, bit2 no epilogue math, bit3 (with 0|1) no weight-ring handshake, bit4 timeline, bit5 tensor-pipe turn taking between the two issuers
+    const int stagger = getenv("XRB_N3_STAGGER") ? atoi(getenv("XRB_N3_STAGGER")) : 0;   // cycles by which pipeline 1 trails pipeline 0 (see the kernel)
     constexpr size_t smem = 1024 + 2 * (size_t)N3_PIPE_A + 2 * (size_t)N3_RING * N3_BLOCK + 256 * sizeof(float) + 8 * (2 * B_PER_PIPE) + 16;
     static_assert(smem <= 232448, "v3 shared memory budget");
     int dev = 0, sms = NUM_SMS; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

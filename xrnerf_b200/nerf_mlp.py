@@ -122,9 +122,22 @@ def pack_nerf_mlp_v2(mlp):
     return torch.from_numpy(np.concatenate(slabs)).to(dev), torch.from_numpy(np.concatenate(biases)).to(dev)
 
 
+def _slab64(w_rows_by_32):
+    """[N,32] float32 -> K-major SWIZZLE_64B bytes (N*64): element (n,k) -> (n>>3)*512 + (n&7)*64 + (((k>>3) ^ ((n>>1)&3))<<4) + (k&7)*2"""
+    n = w_rows_by_32.shape[0]
+    assert w_rows_by_32.shape[1] == 32 and n % 8 == 0
+    h = w_rows_by_32.astype(np.float16)
+    out = np.zeros((n // 8, 8, 4, 8), np.float16)          # [row group][row in group][chunk position][elem]
+    rows = np.arange(n)
+    for c in range(4):
+        pos = c ^ ((rows >> 1) & 3)
+        out[rows >> 3, rows & 7, pos, :] = h[:, c * 8:(c + 1) * 8]
+    return out.reshape(-1).view(np.uint8)
+
+
 def pack_nerf_mlp_v3(mlp):
-    """Image for csrc/nerf_mlp_tc3.cu: half slabs ([N/n_halves x 64]) in the kernel's stream order — per layer, per K-block (AUX block first where a layer
-    reads it), output half 0 then 1. Bias vector: fp32 per-layer biases, Wa[256], ba, padded to 8 floats, then an fp16 copy of the per-layer biases."""
+    """Image for csrc/nerf_mlp_tc3.cu: 16 KB slabs in the kernel's stream order — per layer, per K-block (AUX block first where a layer reads it):
+    the 256-wide layers as two K-halves [256 x 32] (SWIZZLE_64B), views_linears.0 / rgb_linear as one [N x 64] slab (SWIZZLE_128B). Bias vector: fp32 per-layer biases, Wa[256], ba, padded to 8 floats, then an fp16 copy of the per-layer biases."""
     assert len(mlp.pts_linears) == 8 and list(mlp.skips) == [4] and mlp.use_viewdirs and mlp.pts_linears[0].out_features == 256
     ic, icd = mlp.input_ch, mlp.input_ch_dirs
     aux = (ic + 63) // 64
@@ -154,8 +167,11 @@ def pack_nerf_mlp_v3(mlp):
         hw = N // nh
         for blk in blocks:
             assert blk.shape == (N, 64)
-            for half in range(nh):
-                slabs.append(_slab(blk[half * hw:(half + 1) * hw]))
+            if nh == 2:     # N=256 layers: two K-halves [256 x 32] in the 64-byte-swizzle layout (one N=256 MMA pair each: A is read once)
+                for kh in range(2):
+                    slabs.append(_slab64(blk[:, 32 * kh:32 * (kh + 1)]))
+            else:
+                slabs.append(_slab(blk))
         biases.append(b.astype(np.float32))
     layer_bias = np.concatenate(biases)
     Wa, ba = g(mlp.alpha_linear)
