@@ -161,6 +161,11 @@ int xrb_ngp_mlp_backward(const xrb_ngp_config *cfg, const void *table_fp16, cons
  * grad_div first (world size after a sum all-reduce). */
 int xrb_adam_step(float *param, void *param_fp16, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, float grad_div, void *stream);
+/* The same step with the runner's EMAHook (configs/instant_ngp/nerf_blender_local01.py:24: momentum 0.05; mmcv EMAHook.after_train_iter:
+ * ema = (1 - m) * ema + m * param, m = min(momentum, (1 + iter) / (warm_up + iter)) computed by the caller) folded into the pass:
+ * ema f32[n] (NULL = no EMA), initialised by the caller as a copy of param (EMAHook.before_run). */
+int xrb_adam_ema_step(float *param, void *param_fp16, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int step, float grad_div, float *ema, float ema_momentum, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused render of a ray batch (inference): replaces the chain

@@ -147,3 +147,25 @@ def test_adam_step_matches_torch():
         _C.check(_C.lib.xrb_adam_step(_C.ptr(p), _C.ptr(p16), _C.ptr(g * step * 2.0), _C.ptr(m), _C.ptr(v), n, 1e-2, 0.9, 0.99, 1e-15, 1e-6, step, 2.0, _C.stream()))
     assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-6)
     assert torch.equal(p16, p.half())
+
+
+def test_adam_ema_step_matches_torch_and_mmcv_ema_rule():
+    """xrb_adam_ema_step == torch.optim.Adam followed by mmcv's EMAHook.after_train_iter (buffer.mul_(1 - m).add_(m * param),
+    m = min(momentum, (1 + iter) / (warm_up + iter)), buffers initialised as copies): configs/instant_ngp/nerf_blender_local01.py:24."""
+    from xrnerf_b200 import _C
+    torch.manual_seed(1)
+    n = 70001
+    p = torch.randn(n, device='cuda'); g = torch.randn(n, device='cuda') * 0.1
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay=1e-6)
+    ema_ref = p.clone(); ema = p.clone()
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 9):
+        ref.grad = g.clone() * (1 + 0.1 * step)
+        opt.step()
+        it = step - 1
+        mom = min(0.05, (1 + it) / (100 + it))
+        ema_ref.mul_(1 - mom).add_(ref.detach(), alpha=mom)
+        _C.check(_C.lib.xrb_adam_ema_step(_C.ptr(p), None, _C.ptr(g * (1 + 0.1 * step)), _C.ptr(m), _C.ptr(v), n, 1e-2, 0.9, 0.99, 1e-15, 1e-6, step, 1.0, _C.ptr(ema), mom, _C.stream()))
+    assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(ema, ema_ref, rtol=1e-5, atol=1e-6)

@@ -267,7 +267,7 @@ static int launch_bwd(const HashGridDev &g, const void *table, const void *dens,
 
 // ---------------------------------------------------------------------------- fused Adam (+ fp16 shadow refresh)
 __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, __half *__restrict__ p16, const float *__restrict__ grad, float *__restrict__ m, float *__restrict__ v, int64_t n,
-                                                   float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt_inv, float grad_mul) {
+                                                   float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt_inv, float grad_mul, float *__restrict__ ema, float ema_m) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float w = p[i];
         float gval = grad[i] * grad_mul + wd * w;                    // torch.optim.Adam: weight_decay folded into the gradient
@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, __half
         w -= (lr / bc1) * (mi / denom);
         p[i] = w;
         if (p16) p16[i] = __float2half_rn(w);
+        if (ema) ema[i] = ema[i] * (1.f - ema_m) + ema_m * w;        // EMAHook.after_train_iter: buffer.mul_(1 - momentum).add_(momentum, param)
     }
 }
 
@@ -305,13 +306,18 @@ int xrb_ngp_mlp_backward(const xrb_ngp_config *cfg, const void *table_fp16, cons
 
 int xrb_adam_step(float *param, void *param_fp16, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
                   int step, float grad_div, void *stream) {
-    XRB_REQUIRE(n >= 0 && step >= 1 && grad_div != 0.f, "adam_step: bad arguments");
+    return xrb_adam_ema_step(param, param_fp16, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_div, nullptr, 0.f, stream);
+}
+
+int xrb_adam_ema_step(float *param, void *param_fp16, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int step, float grad_div, float *ema, float ema_momentum, void *stream) {
+    XRB_REQUIRE(n >= 0 && step >= 1 && grad_div != 0.f && ema_momentum >= 0.f && ema_momentum <= 1.f, "adam_step: bad arguments");
     if (n == 0) return XRB_OK;
     XRB_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
     double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
     int64_t blocks = (n + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
     adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, (__half *)param_fp16, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
-                                                              (float)(1.0 / sqrt(bc2)), 1.f / grad_div);
+                                                              (float)(1.0 / sqrt(bc2)), 1.f / grad_div, ema, ema_momentum);
     return check_launch("adam_step");
 }
 

@@ -49,7 +49,7 @@ def huber5_grad(rgb, target, delta=0.1):
 
 class NgpTrainer:
     def __init__(self, field, bitfield, n_rays, target_batch_size=1 << 18, aabb=(0.0, 1.0), near=0.05, cone=1.0 / 256, rgb_act=2, dens_act=3,
-                 lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay=1e-6, samples_per_ray_budget=64, group=None):
+                 lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay=1e-6, samples_per_ray_budget=64, group=None, ema_momentum=None, ema_warm_up=100):
         self.f, self.bitfield, self.n_rays, self.T = field, bitfield, n_rays, target_batch_size
         self.aabb, self.near, self.cone, self.rgb_act, self.dens_act = aabb, near, cone, rgb_act, dens_act
         self.lr, self.betas, self.eps, self.wd, self.group = lr, betas, eps, weight_decay, group
@@ -59,6 +59,9 @@ class NgpTrainer:
         self.m = [torch.zeros_like(p) for p in self.params]
         self.v = [torch.zeros_like(p) for p in self.params]
         self.step_n = 0
+        # EMAHook(momentum=0.05) of the reference config (nerf_blender_local01.py:24), folded into the Adam pass; buffers start as copies (EMAHook.before_run)
+        self.ema_momentum, self.ema_warm_up = ema_momentum, ema_warm_up
+        self.ema = [p.detach().clone() for p in self.params] if ema_momentum is not None else [None] * len(self.params)
         cap = n_rays * samples_per_ray_budget
         self.coords = torch.empty((cap, 7), dtype=torch.float32, device=dev)
         self.coords_c = torch.zeros((self.T, 7), dtype=torch.float32, device=dev)
@@ -95,9 +98,11 @@ class NgpTrainer:
         div = self.grads.allreduce(self.group)
         self.step_n += 1
         shadows = [f._table16, f._dens16, f._color16]
-        for p, p16, g_, m, v in zip(self.params, shadows, gv, self.m, self.v):
-            _C.check(_C.lib.xrb_adam_step(_C.ptr(p.data), _C.ptr(p16), _C.ptr(g_), _C.ptr(m), _C.ptr(v), p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                                          self.step_n, div, _C.stream()), 'adam')
+        it = self.step_n - 1                                                            # runner.iter inside after_train_iter
+        mom = 0.0 if self.ema_momentum is None else min(self.ema_momentum, (1 + it) / (self.ema_warm_up + it))
+        for p, p16, g_, m, v, e in zip(self.params, shadows, gv, self.m, self.v, self.ema):
+            _C.check(_C.lib.xrb_adam_ema_step(_C.ptr(p.data), _C.ptr(p16), _C.ptr(g_), _C.ptr(m), _C.ptr(v), p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                                              self.step_n, div, _C.ptr(e), mom, _C.stream()), 'adam')
         _C.check(_C.lib.xrb_ngp_pack_weights(f.cfg, _C.ptr(f.density_params.data), _C.ptr(f.color_params.data), _C.ptr(f._image), _C.stream()), 'pack')
         f._ver = (f.hash_params._version, f.density_params._version, f.color_params._version, f.hash_params.device)  # shadows are current
         return loss
