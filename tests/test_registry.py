@@ -153,3 +153,42 @@ def test_fused_nerf_renderer_matches_network_forward():
     out = NerfRenderer(net, near=2.0, far=6.0, n_samples=s).render(t(o), t(d), t(vd))
     assert (out['coarse_rgb'] - ref['coarse_rgb']).abs().max().item() <= 2e-3
     assert (out['rgb'] - ref['rgb']).abs().max().item() <= 5e-3
+
+
+@pytest.mark.gpu
+def test_hashnerf_fused_inference_matches_chunked_forward(scene):
+    """HashNerfNetwork.batchify_forward(is_test=True): one fused launch for the whole ray set == the reference-shaped path (sample -> mlp -> render per
+    4096-ray chunk) on the same rays, weights, occupancy grid and jitter stream; val_step / test_step keep the reference's keys."""
+    from xrnerf_b200 import registry as R, synth
+    import xrnerf_b200.raymarch_cuda as rm
+    torch.manual_seed(0)
+    net = R.build_network(NGP_MODEL).cuda()
+    n_img = scene['poses'].shape[0]
+    net.sampler.set_data(dict(poses=scene['poses'], focal=np.full((n_img, 2), synth.FOCAL), aabb_scale=1, aabb_range=(0.0, 1.0), metadata=scene['metadata']), dict(H=800, W=800))
+    net.sampler.density_grid_bitfield = torch.from_numpy(scene['bitfield']).cuda()
+    t, d, c = synth.ngp_weights(seed=3, hash_range=0.5, mlp_gain=2.0)
+    with torch.no_grad():
+        net.mlp.field.hash_params.copy_(torch.from_numpy(t).cuda()); net.mlp.field.density_params.copy_(torch.from_numpy(d).cuda()); net.mlp.field.color_params.copy_(torch.from_numpy(c).cuda())
+    data = {'rays_o': torch.from_numpy(scene['rays_o']).cuda(), 'rays_d': torch.from_numpy(scene['rays_d']).cuda(), 'img_ids': torch.from_numpy(scene['img_ids'].astype(np.float32)[:, None]).cuda()}
+    net.chunk, net.bs_data = 4096, 'rays_o'
+    with torch.no_grad():
+        rm.reset_rng()
+        net.fused_inference = False
+        ref = net.batchify_forward(dict(data), is_test=True)
+        rm.reset_rng()
+        net.fused_inference = True
+        got = net.batchify_forward(dict(data), is_test=True)
+    assert got['rgb'].shape == ref['rgb'].shape == (4096, 3) and got['alpha'].shape == (4096, 1)
+    assert (got['rgb'] - ref['rgb']).abs().max().item() <= 2e-3 and (got['alpha'] - ref['alpha']).abs().max().item() <= 2e-3   # fp16 field, fp32 re-association in the scan
+    # val_step over two poses through a val pipeline that hands back precomputed rays
+    H = W = 64
+    def pipeline(item):
+        return dict(data, src_shape=torch.tensor([H, W, 3]))
+    net.set_val_pipeline(pipeline)
+    net.phase = 'train'
+    images = torch.rand((2, H, W, 4), device='cuda')
+    out = net.val_step({'poses': torch.zeros((1, 2, 4, 3)), 'images': images[None]})
+    assert set(out) >= {'rgbs', 'disps', 'gt_imgs', 'elapsed_time', 'psnr'} and len(out['rgbs']) == 2 and out['rgbs'][0].shape == (H, W, 3) and np.isfinite(out['psnr']).all()
+    net.phase = 'test'
+    sp = net.val_step({'poses': torch.zeros((1, 4, 3)), 'idx': 3})
+    assert sp['spiral_rgb'].shape == (H, W, 3) and sp['spiral_alpha'].shape == (H, W, 1) and sp['idx'] == 3

@@ -168,6 +168,62 @@ class HashNerfNetwork(NerfNetwork):
         data, ret = self.render(data, self.sampler, is_test)
         return ret
 
+    def batchify_forward(self, data, is_test=False):
+        """Inference over a whole ray set (hashnerf.py:69-71 via nerf.py:50-69: 4096-ray chunks, each = sample (host sync) -> 3 tcnn launches -> composite).
+        Here the test path is ONE fused launch per call for any number of rays (xrb_ngp_render_fused; no chunk loop, no host sync, no [S,7]/[S,4] buffers);
+        `fused_inference = False` or training falls back to the reference-shaped chunk loop over forward()."""
+        smp = self.sampler
+        if not (is_test and getattr(self, 'fused_inference', True) and data['rays_o'].is_cuda and hasattr(smp, 'aabb_range')):
+            return super().batchify_forward(data, is_test)
+        from ..ngp import NgpRenderer
+        smp.check_device(data)
+        r = getattr(self, '_renderer', None)
+        if r is None:
+            r = self._renderer = NgpRenderer(self.mlp.field, aabb=tuple(float(a) for a in smp.aabb_range), near=smp.near_distance, cone=smp.cone_angle_constant,
+                                             rgb_act=int(smp.rgb_activation), dens_act=int(smp.density_activation), bg=tuple(float(c) for c in self.render.bg_color))
+        import xrnerf_b200.raymarch_cuda as rm
+        r.calls = rm.rng_calls['ray_sampler']               # the same jitter stream the unfused path would use next (hidden static pcg32 of the reference, Q9)
+        rgb, alpha, _ = r.render_fused(data['rays_o'].contiguous().float(), data['rays_d'].contiguous().float(), smp.density_grid_bitfield)
+        rm.rng_calls['ray_sampler'] += 1
+        return {'rgb': rgb.clone(), 'alpha': alpha.clone()}
+
+    def val_step(self, data, optimizer=None, **kwargs):
+        """hashnerf.py:54-93 (rank-0 loop over validation poses) with the image rendered by one launch and the PSNR taken on the device; every rank renders the
+        poses it is given. Returns the reference's keys plus 'psnr'."""
+        if self.phase == 'test':
+            return self.test_step(data, **kwargs)
+        data = {k: unfold_batching(v) for k, v in data.items()}
+        poses, images = data['poses'], data.get('images')
+        rgbs, gt_imgs, psnrs, elapsed = [], [], [], []
+        with torch.no_grad():
+            for i in range(poses.shape[0]):
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                d = self.val_pipeline({'pose': poses[i], 'idx': i})
+                ret = self.batchify_forward(d, is_test=True)
+                rgb = recover_shape(ret['rgb'], d['src_shape'])
+                if images is not None:
+                    alpha = images[i][..., 3:].to(rgb.device)
+                    gt = images[i][..., :3].to(rgb.device) * alpha
+                    rgb = rgb * alpha
+                    gt_imgs.append(gt)
+                    psnrs.append(mse2psnr(img2mse(rgb, gt)))
+                t1.record()
+                rgbs.append(rgb); elapsed.append((t0, t1))
+        torch.cuda.synchronize()
+        return {'rgbs': rgbs, 'disps': [], 'gt_imgs': gt_imgs, 'elapsed_time': [a.elapsed_time(b) * 1e-3 for a, b in elapsed], 'psnr': [float(p.item()) for p in psnrs]}
+
+    def test_step(self, data, **kwargs):
+        """hashnerf.py:95-111: one spiral pose per call."""
+        data = {k: unfold_batching(v) for k, v in data.items()}
+        with torch.no_grad():
+            d = self.val_pipeline({'pose': data['poses'], 'idx': data.get('idx', 0)}) if 'poses' in data and self.val_pipeline is not None else data
+            ret = self.batchify_forward(d, is_test=True)
+        rgb, alpha = ret['rgb'], ret['alpha']
+        if 'src_shape' in d:
+            rgb, alpha = recover_shape(rgb, d['src_shape']), recover_shape(alpha, d['src_shape'])
+        return {'spiral_rgb': rgb, 'spiral_alpha': alpha, 'idx': data.get('idx', 0)}
+
     def train_step(self, data, optimizer, **kwargs):
         data = {k: unfold_batching(v) for k, v in data.items()}
         ret = self.forward(data, is_test=False)
