@@ -31,7 +31,7 @@ constexpr int N3_LAYERS = 11;
 constexpr int N3_MAX_KB = 6;
 constexpr uint32_t N3_BLOCK = 16384;                 // one [128 x 64] fp16 operand block / ring slot
 constexpr uint32_t N3_PIPE_A = 5 * N3_BLOCK;         // H0..H3 + AUX
-constexpr int N3_RING = 4;                           // ONE weight ring of 4 x 16 KB shared by both pipelines (see n3_issue_layer)
+constexpr int N3_RING = 2;
 constexpr int N3_AUX = 4;                            // A block index of AUX
 constexpr int N3_BIAS_LAYERS = 9 * 256 + 128 + 16;   // per-layer biases
 constexpr int N3_BIAS_TOTAL = N3_BIAS_LAYERS + 257;  // + Wa[256] + ba
@@ -84,68 +84,50 @@ __device__ __forceinline__ void n3_bar_arrive(uint32_t id, uint32_t n_threads) {
 __device__ __forceinline__ void n3_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory"); }
 
 // barrier indices inside a pipeline's block of 16
-enum { B_ACC = 5, B_E0 = 6, B_E1 = 7, B_E2 = 8, B_E3 = 9, B_AUXFREE = 10, B_H3FREE = 11, B_PER_PIPE = 16 };
+enum { B_FULL = 0, B_EMPTY = 2, B_ACC = 5, B_E0 = 6, B_E1 = 7, B_E2 = 8, B_E3 = 9, B_AUXFREE = 10, B_H3FREE = 11, B_PER_PIPE = 16 };
 
-struct N3Ctx {            // per-role constants of one pipeline; rb = the shared ring's FULL[4], EMPTY[4] barriers
-    uint64_t *b; uint64_t *rb; uint8_t *A; uint8_t *ring; int p, dbg; uint32_t tmem_p; volatile uint32_t *busy;   // busy[p]: issuer p is inside a layer's issue phase
+struct N3Ctx {            // per-role constants of one pipeline
+    uint64_t *b; uint8_t *A; uint8_t *ring; int p, dbg; uint32_t tmem_p; volatile uint32_t *busy;   // busy[p]: issuer p is inside a layer's issue phase
 };
 
 // ---------------------------------------------------------------------------------------------------- producer (one lane)
-// ONE producer thread feeds ONE ring in the global consumption order  P0.layer0, P1.layer0, P0.layer1, P1.layer1, ...  (both pipelines walk the same
-// layer sequence; pipeline 1 is the follower). Measured before this change (two private 2-slot rings): a pipeline alone could not keep the tensor pipe
-// busy — 32 KB in flight against a ~900-cycle refill (slot release -> producer -> 16 KB TMA -> issuer) gives 36 B/clk where the MMAs eat 64 — and the
-// two pipelines, each throttled to half rate, locked IN PHASE. With the shared ring the active pipeline has all 64 KB in flight, the stream runs on
-// into the follower's slabs while the leader's accumulators drain, and the ring order itself makes the pipelines alternate.
-struct N3PP { uint32_t af; int pending, age; const uint8_t *enc, *enc_next; };   // per-pipeline producer state (AUX block time sharing)
-struct N3Prod { uint32_t g; size_t off; N3PP pp[2]; };
+struct N3Prod { uint32_t it, af; int pending; size_t off; };
 template <bool MIP, int LX>
-__device__ __forceinline__ void n3_produce_layer(const N3Ctx *cs, N3Prod &st, const uint8_t *__restrict__ weight_image, bool act1) {
+__device__ __forceinline__ void n3_produce_layer(const N3Ctx &c, N3Prod &st, const uint8_t *__restrict__ weight_image, const uint8_t *enc, const uint8_t *enc_next) {
     constexpr N3L L = n3_layer<MIP>(LX);
     constexpr uint32_t bytes = (uint32_t)(L.N / L.n_halves) * 128u;
     constexpr int aux_blocks = MIP ? 2 : 1;
     constexpr uint32_t RL = n3_pack(L.reload, 2);
-    const size_t off0 = st.off;
 #pragma unroll 1
-    for (int q = 0; q < (act1 ? 2 : 1); ++q) {
-        const N3Ctx &c = cs[q];
-        N3PP &pp = st.pp[q];
-        size_t off = off0;
+    for (int kb = 0; kb < L.n_kb; ++kb) {
 #pragma unroll 1
-        for (int kb = 0; kb < L.n_kb; ++kb) {
-#pragma unroll 1
-            for (int h = 0; h < L.n_halves; ++h, ++st.g) {
-                const uint32_t slot = st.g % N3_RING, round = st.g / N3_RING;
-                if (!(c.dbg & 8)) {      // (bit3, only with bits 0|1: no ring handshake at all)
-                    if (round > 0) tc::mbar_wait(c.rb + 4 + slot, (round - 1) & 1);
-                    if (c.dbg & 1) n3_arrive(c.rb + slot);
-                    else { tc::mbar_expect_tx(c.rb + slot, bytes); tc::tma_bulk_g2s(c.ring + (size_t)slot * N3_BLOCK, weight_image + off, bytes, c.rb + slot); }
-                }
-                off += bytes;
+        for (int h = 0; h < L.n_halves; ++h, ++st.it) {
+            const uint32_t slot = st.it % N3_RING, round = st.it / N3_RING;
+            if (!(c.dbg & 8)) {      // (bit3, only with bits 0|1: no ring handshake at all)
+                if (round > 0) tc::mbar_wait(c.b + B_EMPTY + slot, (round - 1) & 1);
+                if (c.dbg & 1) n3_arrive(c.b + B_FULL + slot);
+                else { tc::mbar_expect_tx(c.b + B_FULL + slot, bytes); tc::tma_bulk_g2s(c.ring + (size_t)slot * N3_BLOCK, weight_image + st.off, bytes, c.b + B_FULL + slot); }
             }
-            if (pp.pending) {
-                // AUX refill, TWO K-blocks of this pipeline after the one that last read AUX: with 4 ring slots that K-block's slabs have been released by
-                // now (pushing the current one needed their slots or younger ones), so its commit on AUXFREE, issued right behind the slot release, has
-                // landed or is about to — the wait does not stall the weight stream
-                if (pp.age == 1) {
-                    if (pp.pending != 3 || pp.enc_next) {
-                        tc::mbar_wait(c.b + B_AUXFREE, pp.af & 1);
-                        const uint8_t *src = pp.pending == 1 ? pp.enc + (size_t)aux_blocks * N3_BLOCK : pp.pending == 2 ? pp.enc + N3_BLOCK : pp.enc_next;
-                        uint64_t *eb = c.b + (pp.pending == 1 ? B_E1 : pp.pending == 2 ? B_E2 : B_E0);
-                        tc::mbar_expect_tx(eb, N3_BLOCK);
-                        tc::tma_bulk_g2s(c.A + N3_AUX * N3_BLOCK, src, N3_BLOCK, eb);
-                    }
-                    ++pp.af;
-                    pp.pending = 0;
-                } else pp.age = 1;
-            }
-            if ((RL >> (2 * kb)) & 3u) { pp.pending = (int)((RL >> (2 * kb)) & 3u); pp.age = 0; }
+            st.off += bytes;
         }
-        if (q == (act1 ? 1 : 0)) st.off = off;
+        if (st.pending) {
+            // the K-block that last read AUX was issued one K-block ago: its ring slots have been released since, so its commit on AUXFREE (issued right
+            // behind the slot release) has landed or is about to — this wait does not stall the weight stream
+            if (st.pending != 3 || enc_next) {
+                tc::mbar_wait(c.b + B_AUXFREE, st.af & 1);
+                const uint8_t *src = st.pending == 1 ? enc + (size_t)aux_blocks * N3_BLOCK : st.pending == 2 ? enc + N3_BLOCK : enc_next;
+                uint64_t *eb = c.b + (st.pending == 1 ? B_E1 : st.pending == 2 ? B_E2 : B_E0);
+                tc::mbar_expect_tx(eb, N3_BLOCK);
+                tc::tma_bulk_g2s(c.A + N3_AUX * N3_BLOCK, src, N3_BLOCK, eb);
+            }
+            ++st.af;
+        }
+        st.pending = (int)((RL >> (2 * kb)) & 3u);
     }
 }
 template <bool MIP, int... LS>
-__device__ __forceinline__ void n3_produce_tile(std::integer_sequence<int, LS...>, const N3Ctx *cs, N3Prod &st, const uint8_t *__restrict__ weight_image, bool act1) {
-    (n3_produce_layer<MIP, LS>(cs, st, weight_image, act1), ...);
+__device__ __forceinline__ void n3_produce_tile(std::integer_sequence<int, LS...>, const N3Ctx &c, N3Prod &st, const uint8_t *__restrict__ weight_image, const uint8_t *enc, const uint8_t *enc_next) {
+    (n3_produce_layer<MIP, LS>(c, st, weight_image, enc, enc_next), ...);
 }
 
 // ---------------------------------------------------------------------------------------------------- MMA issuer (whole warp walks, lane 0 issues)
@@ -158,13 +140,10 @@ __device__ __forceinline__ bool n3_elect_one() {
     return pred != 0;
 }
 template <bool MIP, int LX>
-__device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &g, bool act1, uint32_t tcount) {
+__device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uint32_t tcount) {
     constexpr N3L L = n3_layer<MIP>(LX);
     constexpr uint32_t idesc = tc::idesc_f16_m128((uint32_t)L.N);
     constexpr uint32_t SRC = n3_pack(L.src, 3), WE = n3_pack(L.wait_enc, 2), RL = n3_pack(L.reload, 2);
-    constexpr uint32_t cnt = (uint32_t)(L.n_kb * L.n_halves);
-    uint32_t it = g + (c.p ? cnt : 0u);              // my slabs in the shared ring's global order: pipeline 0's slabs of this layer, then pipeline 1's
-    g += cnt * (act1 ? 2u : 1u);
     tc::named_bar_sync(5 + c.p, 288);                             // the layer's input rows are in H, the previous accumulator is drained (hardware barrier)
     const bool tr = (c.dbg & 16) && blockIdx.x == 0 && tcount == 2;     // both pipelines' issuers are traced: events 0/1 (pipeline 0), 4/7 (pipeline 1)
     // Tensor-pipe turn taking. Left alone the two pipelines LOCK IN PHASE (timeline r01c: both issuers start every layer within ~20 cycles of each
@@ -196,7 +175,7 @@ __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &g, bool
         for (int h = 0; h < L.n_halves; ++h, ++it) {
             const uint32_t slot = it % N3_RING, round = it / N3_RING;
             if (c.dbg & 8) continue;
-            tc::mbar_wait(c.rb + slot, round & 1);
+            tc::mbar_wait(c.b + B_FULL + slot, round & 1);
             tc::tc_fence_after_sync();
             const uint32_t b0 = b_lo + slot * (N3_BLOCK >> 4);
             if (n3_elect_one()) {
@@ -212,7 +191,7 @@ __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &g, bool
                         for (int k = 0; k < 4; ++k) tc::mma_f16_ss(c.tmem_p, n3_desc(a0 + 2 * k), n3_desc(b0 + 2 * k), idesc, (kb | k) ? 1u : 0u);   // +32 bytes per K step of 16
                     }
                 }
-                tc::mma_commit(c.rb + 4 + slot);
+                tc::mma_commit(c.b + B_EMPTY + slot);
             }
             __syncwarp();
         }
@@ -228,8 +207,8 @@ __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &g, bool
     __syncwarp();
 }
 template <bool MIP, int... LS>
-__device__ __forceinline__ void n3_issue_tile(std::integer_sequence<int, LS...>, const N3Ctx &c, uint32_t &g, bool act1, uint32_t tcount) {
-    (n3_issue_layer<MIP, LS>(c, g, act1, tcount), ...);
+__device__ __forceinline__ void n3_issue_tile(std::integer_sequence<int, LS...>, const N3Ctx &c, uint32_t &it, uint32_t tcount) {
+    (n3_issue_layer<MIP, LS>(c, it, tcount), ...);
 }
 
 // ---------------------------------------------------------------------------------------------------- compute warpgroups
@@ -325,19 +304,18 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
     extern __shared__ uint8_t dyn_smem[];
     uint8_t *base = (uint8_t *)(((uintptr_t)dyn_smem + 1023) & ~(uintptr_t)1023);
     uint8_t *ring_base = base + 2 * N3_PIPE_A;
-    float *alpha_part = (float *)(ring_base + N3_RING * N3_BLOCK);          // [2][128]
+    float *alpha_part = (float *)(ring_base + 2 * N3_RING * N3_BLOCK);          // [2][128]
     uint64_t *bars = (uint64_t *)(alpha_part + 256);
-    uint64_t *rbars = bars + 2 * B_PER_PIPE;                                 // shared ring: FULL[4], EMPTY[4]
-    uint32_t *tmem_slot = (uint32_t *)(rbars + 2 * N3_RING);
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * B_PER_PIPE);
     volatile uint32_t *busy = tmem_slot + 1;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform by construction (uniform registers)
     using Layers = std::make_integer_sequence<int, N3_LAYERS>;
 
     if (threadIdx.x == 0) {
         busy[0] = 0; busy[1] = 0;
-        for (int s = 0; s < 2 * N3_RING; ++s) tc::mbar_init(rbars + s, 1);
         for (int p = 0; p < 2; ++p) {
             uint64_t *b = bars + p * B_PER_PIPE;
+            for (int s = 0; s < N3_RING; ++s) { tc::mbar_init(b + B_FULL + s, 1); tc::mbar_init(b + B_EMPTY + s, 1); }
             tc::mbar_init(b + B_ACC, 1);
             tc::mbar_init(b + B_E0, 1); tc::mbar_init(b + B_E1, 1); tc::mbar_init(b + B_E2, 1); tc::mbar_init(b + B_E3, 1);
             tc::mbar_init(b + B_AUXFREE, 1); tc::mbar_init(b + B_H3FREE, 1);
@@ -352,55 +330,40 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
     const int64_t n_tiles = (n_rows + 127) / 128;
     constexpr uint32_t enc_tile_bytes = (uint32_t)((MIP ? 2 : 1) + 1) * N3_BLOCK;
 
-    auto make_ctx = [&](int p) {
-        N3Ctx c;
-        c.p = p; c.b = bars + p * B_PER_PIPE; c.rb = rbars; c.A = base + (size_t)p * N3_PIPE_A; c.ring = ring_base; c.dbg = dbg;
-        c.tmem_p = tmem + (uint32_t)p * 256u; c.busy = busy;
-        return c;
-    };
-    // tile of pipeline p in round n: (2 * blockIdx.x + p) + n * 2 * gridDim.x; pipeline 0 is the leader: it has a tile whenever pipeline 1 has one
-    const int64_t vstride = (int64_t)gridDim.x * 2, v0 = (int64_t)blockIdx.x * 2;
+    N3Ctx c;
+    c.p = warp >= 16 ? (warp & 1) : (warp >> 3);                 // warps 16,18 / 0-7 -> pipeline 0; 17,19 / 8-15 -> pipeline 1
+    c.b = bars + c.p * B_PER_PIPE; c.A = base + (size_t)c.p * N3_PIPE_A; c.ring = ring_base + (size_t)c.p * N3_RING * N3_BLOCK; c.dbg = dbg;
+    c.tmem_p = tmem + (uint32_t)c.p * 256u; c.busy = busy;
+    const int64_t vcta = (int64_t)blockIdx.x * 2 + c.p, vstride = (int64_t)gridDim.x * 2;
 
     if (warp >= 18) {
-        // ===================================================== MMA issuer of pipeline p = warp - 18
-        const N3Ctx c = make_ctx(warp & 1);
-        (void)stagger;
-        uint32_t g = 0, tcount = 0;
-        for (int64_t t0 = v0; t0 < n_tiles; t0 += vstride) {
-            const bool act1 = t0 + 1 < n_tiles;
-            if (c.p == 0 || act1) { n3_issue_tile<MIP>(Layers{}, c, g, act1, tcount); ++tcount; }
-        }
-    } else if (warp == 16) {
-        // ===================================================== the producer (one lane) of the shared weight ring and of both pipelines' encoding blocks
+        // ===================================================== MMA issuer of pipeline p
+        // Both pipelines start together and would stay IN PHASE (sharing the tensor pipe half/half during their MMA phases and leaving it idle during
+        // both epilogues: the r01c timeline shows 4.1 K-cycle MMA phases = 2 x 2048). The phase offset between them is neutrally stable, so pipeline 1
+        // simply starts half a layer period late and the two alternate: one drains its accumulators while the other one's MMAs run.
+        if (c.p == 1) { const long long t0 = clock64(); while (clock64() - t0 < (long long)stagger) {} }
+        uint32_t it = 0, tcount = 0;
+        for (int64_t tile = vcta; tile < n_tiles; tile += vstride, ++tcount) n3_issue_tile<MIP>(Layers{}, c, it, tcount);
+    } else if (warp >= 16) {
+        // ===================================================== producer of pipeline p
         if (lane == 0) {
-            const N3Ctx cs[2] = {make_ctx(0), make_ctx(1)};
-            N3Prod st{};
+            N3Prod st{0, 0, 0, 0};
             uint32_t n = 0;
-            for (int64_t t0 = v0; t0 < n_tiles; t0 += vstride, ++n) {
-                const bool act1 = t0 + 1 < n_tiles;
-                for (int q = 0; q < (act1 ? 2 : 1); ++q) {
-                    const int64_t tile = t0 + q, next = tile + vstride;
-                    N3PP &pp = st.pp[q];
-                    pp.enc = enc_image + (size_t)tile * enc_tile_bytes;
-                    pp.enc_next = next < n_tiles ? enc_image + (size_t)next * enc_tile_bytes : nullptr;
-                    const N3Ctx &c = cs[q];
-                    if (n == 0) { tc::mbar_expect_tx(c.b + B_E0, N3_BLOCK); tc::tma_bulk_g2s(c.A + N3_AUX * N3_BLOCK, pp.enc, N3_BLOCK, c.b + B_E0); }   // later tiles: loaded behind the previous tile's direction block
-                    if (MIP) {
-                        if (n > 0) tc::mbar_wait(c.b + B_H3FREE, (n - 1) & 1);          // views_linears.0 of the previous tile has read the feature block in H3
-                        tc::mbar_expect_tx(c.b + B_E3, N3_BLOCK);
-                        tc::tma_bulk_g2s(c.A + 3 * N3_BLOCK, pp.enc + N3_BLOCK, N3_BLOCK, c.b + B_E3);
-                    }
+            for (int64_t tile = vcta; tile < n_tiles; tile += vstride, ++n) {
+                const uint8_t *enc = enc_image + (size_t)tile * enc_tile_bytes;
+                const uint8_t *enc_next = tile + vstride < n_tiles ? enc_image + (size_t)(tile + vstride) * enc_tile_bytes : nullptr;
+                if (n == 0) { tc::mbar_expect_tx(c.b + B_E0, N3_BLOCK); tc::tma_bulk_g2s(c.A + N3_AUX * N3_BLOCK, enc, N3_BLOCK, c.b + B_E0); }   // later tiles: loaded behind the previous tile's direction block
+                if (MIP) {
+                    if (n > 0) tc::mbar_wait(c.b + B_H3FREE, (n - 1) & 1);          // views_linears.0 of the previous tile has read the feature block in H3
+                    tc::mbar_expect_tx(c.b + B_E3, N3_BLOCK);
+                    tc::tma_bulk_g2s(c.A + 3 * N3_BLOCK, enc + N3_BLOCK, N3_BLOCK, c.b + B_E3);
                 }
-                st.off = 0;
-                n3_produce_tile<MIP>(Layers{}, cs, st, weight_image, act1);
+                st.off = 0; st.pending = 0;
+                n3_produce_tile<MIP>(Layers{}, c, st, weight_image, enc, enc_next);
             }
         }
-    } else if (warp == 17) {
-        // (idle: the second producer of the private-ring version)
     } else {
         // ===================================================== compute warpgroups WG(p, cc): thread == row, cc == column half
-        const N3Ctx c = make_ctx(warp >> 3);                        // warps 0-7 -> pipeline 0, 8-15 -> pipeline 1
-        const int64_t vcta = v0 + c.p;
         N3Comp s;
         s.cc = (warp >> 2) & 1; s.warp = warp; s.lane = lane;
         s.apart = alpha_part + c.p * 128;
@@ -446,7 +409,7 @@ int xrb_nerf_mlp_forward_v3(const void *weight_image, const float *bias, const v
     const bool mip = input_ch > 64;
     const int dbg = getenv("XRB_NM_DBG") ? atoi(getenv("XRB_NM_DBG")) : 0;   // attribution experiments: bit0 no weight TMA, bit1 no MMAs, bit2 no epilogue math, bit3 (with 0|1) no weight-ring handshake, bit4 timeline, bit5 tensor-pipe turn taking between the two issuers
     const int stagger = getenv("XRB_N3_STAGGER") ? atoi(getenv("XRB_N3_STAGGER")) : 0;   // cycles by which pipeline 1 trails pipeline 0 (see the kernel)
-    constexpr size_t smem = 1024 + 2 * (size_t)N3_PIPE_A + (size_t)N3_RING * N3_BLOCK + 256 * sizeof(float) + 8 * (2 * B_PER_PIPE + 2 * N3_RING) + 16;
+    constexpr size_t smem = 1024 + 2 * (size_t)N3_PIPE_A + 2 * (size_t)N3_RING * N3_BLOCK + 256 * sizeof(float) + 8 * (2 * B_PER_PIPE) + 16;
     static_assert(smem <= 232448, "v3 shared memory budget");
     int dev = 0, sms = NUM_SMS; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t n_tiles = (n_rows + 127) / 128, pairs = (n_tiles + 1) / 2;
