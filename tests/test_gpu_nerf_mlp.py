@@ -189,3 +189,22 @@ def test_nerf_mlp_v3_two_tiles_in_flight_matches_v2_and_fp32(cfg, n_rows, monkey
     with torch.no_grad():
         ref = _ref_fp32(mlp, emb[:4096])
     assert (out['3'][:4096] - ref).abs().max().item() <= 2e-2 * ref.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize('cfg,n_rows', [(NERF_MLP, 1), (NERF_MLP, 5 * 128 + 3), (NERF_MLP, 2 * 296 * 128 + 77), (MIP_MLP, 2 * 296 * 128 + 300)])
+def test_nerf_mlp_v3_cta_pair_multicast_matches_single_cta(cfg, n_rows, monkeypatch):
+    """XRB_N3_CLUSTER=1: clusters of two CTAs, rank 0 loads every weight slab once and the TMA multicasts it into both CTAs' rings (phantom tiles keep the
+    pair in lock step at the ragged end). Same arithmetic, same order: identical results."""
+    from xrnerf_b200 import registry as R
+    from xrnerf_b200.nerf_mlp import nerf_mlp_forward
+    torch.manual_seed(11)
+    mlp = R.build_mlp(cfg).cuda()
+    emb = torch.randn((n_rows, mlp.input_ch + mlp.input_ch_dirs), device='cuda').clamp_(-1, 1)
+    monkeypatch.setenv('XRB_NERF_MLP_V', '3')
+    image, bias = mlp._packed()
+    out = {}
+    for cl in ('0', '1'):
+        monkeypatch.setenv('XRB_N3_CLUSTER', cl)
+        out[cl] = nerf_mlp_forward(image, bias, emb, mlp.input_ch, mlp.input_ch_dirs, version=3).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(out['0'], out['1'])

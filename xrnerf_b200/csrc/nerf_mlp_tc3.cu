@@ -79,20 +79,32 @@ __device__ __forceinline__ uint64_t n3_desc(uint32_t lo) { return ((uint64_t)((1
 __device__ __forceinline__ uint64_t n3_desc64(uint32_t lo) { return ((uint64_t)((512u >> 4) | (1u << 14) | (4u << 29)) << 32) | (uint64_t)lo; }   // K-major SWIZZLE_64B: 8-row atoms of 64-byte rows, 512 B apart
 __device__ __forceinline__ uint32_t n3_desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
 
+// ---- CTA-pair mode (template CL): the two CTAs of a cluster walk identical schedules; rank 0's producers load every weight slab ONCE and the TMA
+// multicasts it into both CTAs' rings (same offsets), halving the weight bytes read out of L2 — the measured ceiling of the single-CTA version (8.6 TB/s).
+__device__ __forceinline__ uint32_t n3_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void n3_cluster_sync() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void n3_tma_bulk_g2s_mc(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes),
+                 "r"(tc::smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void n3_commit_mc(uint64_t *bar, uint16_t mask) {   // arrives on the barrier at this offset in every CTA of the mask
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(tc::smem_u32(bar)), "h"(mask) : "memory");
+}
+
 __device__ long long n3_trace_buf[8][16];   // developer timeline (dbg bit4): [event][layer] clock64 of block 0 / pipeline 0 / its 3rd tile
 __device__ __forceinline__ void n3_bar_arrive(uint32_t id, uint32_t n_threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n_threads) : "memory"); }
 __device__ __forceinline__ void n3_arrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory"); }
 
 // barrier indices inside a pipeline's block of 16
-enum { B_FULL = 0, B_EMPTY = 2, B_ACC = 5, B_E0 = 6, B_E1 = 7, B_E2 = 8, B_E3 = 9, B_AUXFREE = 10, B_H3FREE = 11, B_PER_PIPE = 16 };
+enum { B_FULL = 0, B_EMPTY = 2, B_ACC = 5, B_E0 = 6, B_E1 = 7, B_E2 = 8, B_E3 = 9, B_AUXFREE = 10, B_H3FREE = 11, B_LEMPTY = 12, B_PER_PIPE = 16 };   // B_LEMPTY[2]: CTA-pair mode, rank 1: my own slot release (re-arms FULL)
 
 struct N3Ctx {            // per-role constants of one pipeline
-    uint64_t *b; uint8_t *A; uint8_t *ring; int p, dbg; uint32_t tmem_p; volatile uint32_t *busy;   // busy[p]: issuer p is inside a layer's issue phase
+    uint64_t *b; uint8_t *A; uint8_t *ring; int p, dbg, crank; uint32_t tmem_p; volatile uint32_t *busy;   // busy[p]: issuer p is inside a layer's issue phase
 };
 
 // ---------------------------------------------------------------------------------------------------- producer (one lane)
 struct N3Prod { uint32_t it, af; int pending; size_t off; };
-template <bool MIP, int LX>
+template <bool MIP, bool CL, int LX>
 __device__ __forceinline__ void n3_produce_layer(const N3Ctx &c, N3Prod &st, const uint8_t *__restrict__ weight_image, const uint8_t *enc, const uint8_t *enc_next) {
     constexpr N3L L = n3_layer<MIP>(LX);
     constexpr uint32_t bytes = (uint32_t)(L.N / L.n_halves) * 128u;
@@ -103,7 +115,13 @@ __device__ __forceinline__ void n3_produce_layer(const N3Ctx &c, N3Prod &st, con
 #pragma unroll 1
         for (int h = 0; h < L.n_halves; ++h, ++st.it) {
             const uint32_t slot = st.it % N3_RING, round = st.it / N3_RING;
-            if (!(c.dbg & 8)) {      // (bit3, only with bits 0|1: no ring handshake at all)
+            if (CL) {
+                // rank 0 loads for both CTAs once BOTH have released the slot (EMPTY counts 2: my issuer's commit + the peer's multicast commit);
+                // rank 1 only re-arms its own FULL barrier when its own issuer has released the slot (the bytes arrive from rank 0's multicast)
+                if (round > 0) tc::mbar_wait(c.b + (c.crank ? B_LEMPTY : B_EMPTY) + slot, (round - 1) & 1);
+                tc::mbar_expect_tx(c.b + B_FULL + slot, bytes);
+                if (c.crank == 0) n3_tma_bulk_g2s_mc(c.ring + (size_t)slot * N3_BLOCK, weight_image + st.off, bytes, c.b + B_FULL + slot, (uint16_t)3);
+            } else if (!(c.dbg & 8)) {      // (bit3, only with bits 0|1: no ring handshake at all)
                 if (round > 0) tc::mbar_wait(c.b + B_EMPTY + slot, (round - 1) & 1);
                 if (c.dbg & 1) n3_arrive(c.b + B_FULL + slot);
                 else { tc::mbar_expect_tx(c.b + B_FULL + slot, bytes); tc::tma_bulk_g2s(c.ring + (size_t)slot * N3_BLOCK, weight_image + st.off, bytes, c.b + B_FULL + slot); }
@@ -125,9 +143,9 @@ __device__ __forceinline__ void n3_produce_layer(const N3Ctx &c, N3Prod &st, con
         st.pending = (int)((RL >> (2 * kb)) & 3u);
     }
 }
-template <bool MIP, int... LS>
+template <bool MIP, bool CL, int... LS>
 __device__ __forceinline__ void n3_produce_tile(std::integer_sequence<int, LS...>, const N3Ctx &c, N3Prod &st, const uint8_t *__restrict__ weight_image, const uint8_t *enc, const uint8_t *enc_next) {
-    (n3_produce_layer<MIP, LS>(c, st, weight_image, enc, enc_next), ...);
+    (n3_produce_layer<MIP, CL, LS>(c, st, weight_image, enc, enc_next), ...);
 }
 
 // ---------------------------------------------------------------------------------------------------- MMA issuer (whole warp walks, lane 0 issues)
@@ -139,7 +157,7 @@ __device__ __forceinline__ bool n3_elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
-template <bool MIP, int LX>
+template <bool MIP, bool CL, int LX>
 __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uint32_t tcount) {
     constexpr N3L L = n3_layer<MIP>(LX);
     constexpr uint32_t idesc = tc::idesc_f16_m128((uint32_t)L.N);
@@ -191,7 +209,8 @@ __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uin
                         for (int k = 0; k < 4; ++k) tc::mma_f16_ss(c.tmem_p, n3_desc(a0 + 2 * k), n3_desc(b0 + 2 * k), idesc, (kb | k) ? 1u : 0u);   // +32 bytes per K step of 16
                     }
                 }
-                tc::mma_commit(c.b + B_EMPTY + slot);
+                if (CL && c.crank) { tc::mma_commit(c.b + B_LEMPTY + slot); n3_commit_mc(c.b + B_EMPTY + slot, (uint16_t)1); }   // my producer may re-arm; rank 0 may reload
+                else tc::mma_commit(c.b + B_EMPTY + slot);
             }
             __syncwarp();
         }
@@ -206,9 +225,9 @@ __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uin
     }
     __syncwarp();
 }
-template <bool MIP, int... LS>
+template <bool MIP, bool CL, int... LS>
 __device__ __forceinline__ void n3_issue_tile(std::integer_sequence<int, LS...>, const N3Ctx &c, uint32_t &it, uint32_t tcount) {
-    (n3_issue_layer<MIP, LS>(c, it, tcount), ...);
+    (n3_issue_layer<MIP, CL, LS>(c, it, tcount), ...);
 }
 
 // ---------------------------------------------------------------------------------------------------- compute warpgroups
@@ -298,7 +317,7 @@ __device__ __forceinline__ void n3_epilogue_tile(std::integer_sequence<int, LS..
     (n3_epilogue_layer<MIP, LS>(c, s), ...);
 }
 
-template <bool MIP>
+template <bool MIP, bool CL>
 __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, int stagger, const uint8_t *__restrict__ weight_image, const float *__restrict__ bias_g, const uint8_t *__restrict__ enc_image,
                                                                       int64_t n_rows, float *__restrict__ raw) {
     extern __shared__ uint8_t dyn_smem[];
@@ -315,7 +334,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
         busy[0] = 0; busy[1] = 0;
         for (int p = 0; p < 2; ++p) {
             uint64_t *b = bars + p * B_PER_PIPE;
-            for (int s = 0; s < N3_RING; ++s) { tc::mbar_init(b + B_FULL + s, 1); tc::mbar_init(b + B_EMPTY + s, 1); }
+            for (int s = 0; s < N3_RING; ++s) { tc::mbar_init(b + B_FULL + s, 1); tc::mbar_init(b + B_EMPTY + s, CL ? 2 : 1); tc::mbar_init(b + B_LEMPTY + s, 1); }
             tc::mbar_init(b + B_ACC, 1);
             tc::mbar_init(b + B_E0, 1); tc::mbar_init(b + B_E1, 1); tc::mbar_init(b + B_E2, 1); tc::mbar_init(b + B_E3, 1);
             tc::mbar_init(b + B_AUXFREE, 1); tc::mbar_init(b + B_H3FREE, 1);
@@ -325,6 +344,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
     if (warp == 16) tc::tmem_alloc<512>(tmem_slot);
     tc::tc_fence_before_sync();
     __syncthreads();
+    if (CL) n3_cluster_sync();                                   // the peer's barriers are initialised before anything of mine can signal them
     tc::tc_fence_after_sync();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int64_t n_tiles = (n_rows + 127) / 128;
@@ -333,8 +353,12 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
     N3Ctx c;
     c.p = warp >= 16 ? (warp & 1) : (warp >> 3);                 // warps 16,18 / 0-7 -> pipeline 0; 17,19 / 8-15 -> pipeline 1
     c.b = bars + c.p * B_PER_PIPE; c.A = base + (size_t)c.p * N3_PIPE_A; c.ring = ring_base + (size_t)c.p * N3_RING * N3_BLOCK; c.dbg = dbg;
-    c.tmem_p = tmem + (uint32_t)c.p * 256u; c.busy = busy;
+    c.tmem_p = tmem + (uint32_t)c.p * 256u; c.busy = busy; c.crank = CL ? (int)n3_cluster_rank() : 0;
+    // tile of (round r, CTA, pipeline p) = (r * gridDim.x + blockIdx.x) * 2 + p. EVERY pipeline of the grid walks the same number of rounds; a tile index
+    // past the end is a PHANTOM tile: it is computed on the last tile's encodings and writes nothing. (The two CTAs of a pair must consume the multicast
+    // weight stream in lock step, so neither may stop early; without clusters the phantom work is at most one tile per pipeline.)
     const int64_t vcta = (int64_t)blockIdx.x * 2 + c.p, vstride = (int64_t)gridDim.x * 2;
+    const int64_t rounds = (n_tiles + vstride - 1) / vstride;
 
     if (warp >= 18) {
         // ===================================================== MMA issuer of pipeline p
@@ -343,15 +367,16 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
         // simply starts half a layer period late and the two alternate: one drains its accumulators while the other one's MMAs run.
         if (c.p == 1) { const long long t0 = clock64(); while (clock64() - t0 < (long long)stagger) {} }
         uint32_t it = 0, tcount = 0;
-        for (int64_t tile = vcta; tile < n_tiles; tile += vstride, ++tcount) n3_issue_tile<MIP>(Layers{}, c, it, tcount);
+        for (int64_t r = 0; r < rounds; ++r, ++tcount) n3_issue_tile<MIP, CL>(Layers{}, c, it, tcount);
     } else if (warp >= 16) {
         // ===================================================== producer of pipeline p
         if (lane == 0) {
             N3Prod st{0, 0, 0, 0};
             uint32_t n = 0;
-            for (int64_t tile = vcta; tile < n_tiles; tile += vstride, ++n) {
+            for (int64_t r = 0; r < rounds; ++r, ++n) {
+                const int64_t tile = min(vcta + r * vstride, n_tiles - 1), tile_next = min(vcta + (r + 1) * vstride, n_tiles - 1);   // phantom tiles re-read the last tile's encodings
                 const uint8_t *enc = enc_image + (size_t)tile * enc_tile_bytes;
-                const uint8_t *enc_next = tile + vstride < n_tiles ? enc_image + (size_t)(tile + vstride) * enc_tile_bytes : nullptr;
+                const uint8_t *enc_next = r + 1 < rounds ? enc_image + (size_t)tile_next * enc_tile_bytes : nullptr;
                 if (n == 0) { tc::mbar_expect_tx(c.b + B_E0, N3_BLOCK); tc::tma_bulk_g2s(c.A + N3_AUX * N3_BLOCK, enc, N3_BLOCK, c.b + B_E0); }   // later tiles: loaded behind the previous tile's direction block
                 if (MIP) {
                     if (n > 0) tc::mbar_wait(c.b + B_H3FREE, (n - 1) & 1);          // views_linears.0 of the previous tile has read the feature block in H3
@@ -359,7 +384,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
                     tc::tma_bulk_g2s(c.A + 3 * N3_BLOCK, enc + N3_BLOCK, N3_BLOCK, c.b + B_E3);
                 }
                 st.off = 0; st.pending = 0;
-                n3_produce_tile<MIP>(Layers{}, c, st, weight_image, enc, enc_next);
+                n3_produce_tile<MIP, CL>(Layers{}, c, st, weight_image, enc, enc_next);
             }
         }
     } else {
@@ -373,10 +398,11 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
         s.bias_g = bias_g; s.raw = raw;
         s.acc_phase = 0;
         uint32_t tcnt = 0;
-        for (int64_t tile = vcta; tile < n_tiles; tile += vstride, ++tcnt) {
+        for (int64_t r = 0; r < rounds; ++r, ++tcnt) {
+            const int64_t tile = vcta + r * vstride;
             s.tr = (dbg & 16) && blockIdx.x == 0 && c.p == 0 && tcnt == 2;
             s.i = tile * 128 + s.row;
-            s.valid = s.i < n_rows;
+            s.valid = s.i < n_rows;                                  // false for every row of a phantom tile
             tc::tc_fence_before_sync();
             __syncwarp();
             n3_bar_arrive(5 + c.p, 288);                             // my reads of the previous tile's accumulators are done (hardware barrier towards the issuer warp)
@@ -386,6 +412,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
     }
     tc::tc_fence_before_sync();
     __syncthreads();
+    if (CL) n3_cluster_sync();                                   // nobody leaves while the peer may still signal one of its barriers
     if (warp == 16) tc::tmem_dealloc<512>(tmem);
 }
 
@@ -413,13 +440,32 @@ int xrb_nerf_mlp_forward_v3(const void *weight_image, const float *bias, const v
     static_assert(smem <= 232448, "v3 shared memory budget");
     int dev = 0, sms = NUM_SMS; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t n_tiles = (n_rows + 127) / 128, pairs = (n_tiles + 1) / 2;
-    const int grid = (int)(pairs < sms ? pairs : sms);
-    if (mip) {
-        cudaFuncSetAttribute(nerf_mlp_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        nerf_mlp_tc3_kernel<true><<<grid, N3_THREADS, smem, (cudaStream_t)stream>>>(dbg, stagger, (const uint8_t *)weight_image, bias, (const uint8_t *)enc_image, n_rows, raw);
+    int grid = (int)(pairs < sms ? pairs : sms);
+    const bool cluster = getenv("XRB_N3_CLUSTER") ? atoi(getenv("XRB_N3_CLUSTER")) != 0 : false;   // CTA pairs with multicast weight loads (see the kernel)
+    if (cluster) {
+        grid = (grid + 1) & ~1;                                   // whole pairs; a CTA without real tiles walks phantom tiles
+        if (grid > sms) grid = sms & ~1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(N3_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension; attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const uint8_t *wi = (const uint8_t *)weight_image, *ei = (const uint8_t *)enc_image;
+        cudaError_t e;
+        if (mip) {
+            cudaFuncSetAttribute(nerf_mlp_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaLaunchKernelEx(&cfg, nerf_mlp_tc3_kernel<true, true>, dbg, stagger, wi, bias, ei, n_rows, raw);
+        } else {
+            cudaFuncSetAttribute(nerf_mlp_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaLaunchKernelEx(&cfg, nerf_mlp_tc3_kernel<false, true>, dbg, stagger, wi, bias, ei, n_rows, raw);
+        }
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -100; }
+    } else if (mip) {
+        cudaFuncSetAttribute(nerf_mlp_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        nerf_mlp_tc3_kernel<true, false><<<grid, N3_THREADS, smem, (cudaStream_t)stream>>>(dbg, stagger, (const uint8_t *)weight_image, bias, (const uint8_t *)enc_image, n_rows, raw);
     } else {
-        cudaFuncSetAttribute(nerf_mlp_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        nerf_mlp_tc3_kernel<false><<<grid, N3_THREADS, smem, (cudaStream_t)stream>>>(dbg, stagger, (const uint8_t *)weight_image, bias, (const uint8_t *)enc_image, n_rows, raw);
+        cudaFuncSetAttribute(nerf_mlp_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        nerf_mlp_tc3_kernel<false, false><<<grid, N3_THREADS, smem, (cudaStream_t)stream>>>(dbg, stagger, (const uint8_t *)weight_image, bias, (const uint8_t *)enc_image, n_rows, raw);
     }
     return check_launch("nerf_mlp_forward_v3");
 }
