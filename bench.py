@@ -502,7 +502,10 @@ def run_ours(args):
             'e2e': {'value': world * N_RAYS * K / (e2e_ms * 1e-3), 'unit': 'rays/s', 'h2d_bytes_per_step': N_RAYS * 24, 'd2h_bytes_per_step': N_RAYS * 16,
                     'ms_per_step': e2e_ms / K, 'host_wall_ms_per_step': e2e_wall_ms / K},
             'gpu_launches': head['gpu_launches_per_step'] * K,
-            'roofline': dict(head['roofline'], traffic=None, peak_source=peak_src,
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of that kernel at this workload, from the committed ncu --set full captures
+            # (profiles/r01b_ngp_field_tc_ncu.md: 41.88 MB + 1.64 MB; profiles/r01b_ngp_render_fused_ncu.md: 27.80 MB + 0.04 MB) - far below the algorithmic
+            # bytes because the gather is served by L2/L1
+            'roofline': dict(head['roofline'], traffic=(27.80e6 + 0.04e6) if use_fused else (41.88e6 + 1.64e6), traffic_source='ncu --set full capture committed under profiles/ (r01b), bytes per launch', peak_source=peak_src,
                              note='hash table (24.4 MB fp16) is L2-resident by design: the gather is served by L1/L2, so DRAM traffic (ncu, profiles/) is far below the algorithmic bytes'),
             'paths': {'chain': chain, 'fused': fused},
             'cpu_baseline': {'value': cpu_rate, 'unit': 'rays/s', 'cores': cores, 'kind': kind, 'sample': sample},

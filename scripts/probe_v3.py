@@ -38,13 +38,12 @@ for v in ((3,) if os.environ.get('PROBE_V3_ONLY') else (3, 2)):
     if only:
         break
 
-for cl in ('0', '1'):
-    for dbg in (0, 32):
-        os.environ['XRB_N3_CLUSTER'] = cl; os.environ['XRB_NM_DBG'] = str(dbg)
-        image, bias = packs[3]
-        t = timeit(lambda: nerf_mlp_forward_tiles(image, bias, enc, rows, 63, 27, raw, version=3), n=10)
-        print(f'v3 cluster={cl} turn-taking={"on" if dbg else "off"}: {t:.3f} ms -> {flop / t / 1e9:.1f} TFLOP/s-equivalent', flush=True)
-os.environ['XRB_N3_CLUSTER'] = os.environ.get('PROBE_CLUSTER', '0')
+for sr in ('0', '1'):
+    os.environ['XRB_N3_SHARED_RING'] = sr; os.environ['XRB_NM_DBG'] = '0'
+    image, bias = packs[3]
+    t = timeit(lambda: nerf_mlp_forward_tiles(image, bias, enc, rows, 63, 27, raw, version=3), n=10)
+    print(f'v3 shared_ring={sr}: {t:.3f} ms -> {flop / t / 1e9:.1f} TFLOP/s-equivalent', flush=True)
+os.environ['XRB_N3_SHARED_RING'] = os.environ.get('PROBE_SR', '0')
 for stg in ():
     os.environ['XRB_NM_DBG'] = '0'; os.environ['XRB_N3_STAGGER'] = str(stg)
     image, bias = packs[3]
@@ -54,7 +53,7 @@ os.environ['XRB_N3_STAGGER'] = '3000'
 # ---- timeline of one tile (dbg bit4): issuer / poller / compute time stamps per layer, in cycles relative to the layer-0 issuer start
 import ctypes, numpy as np
 _C.lib.xrb_internal_n3_trace.argtypes = [ctypes.c_void_p]
-for dbg, stg in ((16, 0),):
+for dbg, stg in [(int(x), 0) for x in os.environ.get('PROBE_TIMELINES', '16').split(',')]:
     os.environ['XRB_N3_STAGGER'] = str(stg)
     os.environ['XRB_NM_DBG'] = str(dbg)
     image, bias = packs[3]

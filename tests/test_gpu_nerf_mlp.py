@@ -206,5 +206,8 @@ def test_nerf_mlp_v3_cta_pair_multicast_matches_single_cta(cfg, n_rows, monkeypa
     for cl in ('0', '1'):
         monkeypatch.setenv('XRB_N3_CLUSTER', cl)
         out[cl] = nerf_mlp_forward(image, bias, emb, mlp.input_ch, mlp.input_ch_dirs, version=3).clone()
+    monkeypatch.setenv('XRB_N3_CLUSTER', '0')
+    monkeypatch.setenv('XRB_N3_SHARED_RING', '1')             # one 4-slot ring consumed in the global order P0.layer, P1.layer, ... (csrc/nerf_mlp_tc3.cu, MD 2)
+    out['sr'] = nerf_mlp_forward(image, bias, emb, mlp.input_ch, mlp.input_ch_dirs, version=3).clone()
     torch.cuda.synchronize()
-    assert torch.equal(out['0'], out['1'])
+    assert torch.equal(out['0'], out['1']) and torch.equal(out['0'], out['sr'])

@@ -99,53 +99,82 @@ __device__ __forceinline__ void n3_arrive(uint64_t *bar) { asm volatile("mbarrie
 enum { B_FULL = 0, B_EMPTY = 2, B_ACC = 5, B_E0 = 6, B_E1 = 7, B_E2 = 8, B_E3 = 9, B_AUXFREE = 10, B_H3FREE = 11, B_LEMPTY = 12, B_PER_PIPE = 16 };   // B_LEMPTY[2]: CTA-pair mode, rank 1: my own slot release (re-arms FULL)
 
 struct N3Ctx {            // per-role constants of one pipeline
-    uint64_t *b; uint8_t *A; uint8_t *ring; int p, dbg, crank; uint32_t tmem_p; volatile uint32_t *busy;   // busy[p]: issuer p is inside a layer's issue phase
+    uint64_t *b; uint64_t *bars0; uint8_t *A; uint8_t *ring; uint8_t *ring0; int p, dbg, crank; uint32_t tmem_p; volatile uint32_t *busy;   // busy[p]: issuer p is inside a layer's issue phase
 };
 
 // ---------------------------------------------------------------------------------------------------- producer (one lane)
-struct N3Prod { uint32_t it, af; int pending; size_t off; };
-template <bool MIP, bool CL, int LX>
+struct N3Prod { uint32_t it, af; int pending, age; size_t off; };
+// Ring barriers of the SHARED ring (MD == 2): 4 slots = the two pipelines' private slot pairs, back to back; slot s uses pipeline (s>>1)'s barrier pair (s&1).
+__device__ __forceinline__ uint64_t *n3_sr_full(const N3Ctx &c, uint32_t slot) { return c.bars0 + (slot >> 1) * B_PER_PIPE + B_FULL + (slot & 1u); }
+__device__ __forceinline__ uint64_t *n3_sr_empty(const N3Ctx &c, uint32_t slot) { return c.bars0 + (slot >> 1) * B_PER_PIPE + B_EMPTY + (slot & 1u); }
+
+// MD == 0: private 2-slot rings. MD == 1: CTA pairs, rank 0 multicasts every slab into both CTAs' private rings. MD == 2: ONE 4-slot ring consumed in the
+// global order  P0.layer0, P1.layer0, P0.layer1, ...  (every pipeline walks the same number of rounds, phantom tiles at the ragged end): the pipeline whose
+// turn it is has 64 KB of weights in flight instead of 32 — measured: alone on the tensor pipe a pipeline's MMA phase is 3.9 K cycles with the weight TMA and
+// 2.6 K without (2-slot ring x ~900-cycle refill) — and the turn order makes the two pipelines alternate instead of locking in phase.
+template <bool MIP, int MD, int LX>
 __device__ __forceinline__ void n3_produce_layer(const N3Ctx &c, N3Prod &st, const uint8_t *__restrict__ weight_image, const uint8_t *enc, const uint8_t *enc_next) {
     constexpr N3L L = n3_layer<MIP>(LX);
+    constexpr bool CL = MD == 1, SR = MD == 2;
     constexpr uint32_t bytes = (uint32_t)(L.N / L.n_halves) * 128u;
     constexpr int aux_blocks = MIP ? 2 : 1;
     constexpr uint32_t RL = n3_pack(L.reload, 2);
+    constexpr uint32_t cnt = (uint32_t)(L.n_kb * L.n_halves);
+    uint32_t sr_it = 0;
+    if (SR) {
+        sr_it = st.it + (c.p ? cnt : 0u);                  // my slabs in the global order
+        st.it += 2 * cnt;
+        while (c.busy[3] != sr_it) {}                      // producers push in the global order too (a barrier wait must never be two ring rounds ahead)
+    }
 #pragma unroll 1
     for (int kb = 0; kb < L.n_kb; ++kb) {
 #pragma unroll 1
-        for (int h = 0; h < L.n_halves; ++h, ++st.it) {
-            const uint32_t slot = st.it % N3_RING, round = st.it / N3_RING;
-            if (CL) {
-                // rank 0 loads for both CTAs once BOTH have released the slot (EMPTY counts 2: my issuer's commit + the peer's multicast commit);
-                // rank 1 only re-arms its own FULL barrier when its own issuer has released the slot (the bytes arrive from rank 0's multicast)
-                if (round > 0) tc::mbar_wait(c.b + (c.crank ? B_LEMPTY : B_EMPTY) + slot, (round - 1) & 1);
-                tc::mbar_expect_tx(c.b + B_FULL + slot, bytes);
-                if (c.crank == 0) n3_tma_bulk_g2s_mc(c.ring + (size_t)slot * N3_BLOCK, weight_image + st.off, bytes, c.b + B_FULL + slot, (uint16_t)3);
-            } else if (!(c.dbg & 8)) {      // (bit3, only with bits 0|1: no ring handshake at all)
-                if (round > 0) tc::mbar_wait(c.b + B_EMPTY + slot, (round - 1) & 1);
-                if (c.dbg & 1) n3_arrive(c.b + B_FULL + slot);
-                else { tc::mbar_expect_tx(c.b + B_FULL + slot, bytes); tc::tma_bulk_g2s(c.ring + (size_t)slot * N3_BLOCK, weight_image + st.off, bytes, c.b + B_FULL + slot); }
+        for (int h = 0; h < L.n_halves; ++h) {
+            if (SR) {
+                const uint32_t slot = sr_it % 4u, round = sr_it / 4u;
+                if (round > 0) tc::mbar_wait(n3_sr_empty(c, slot), (round - 1) & 1);
+                tc::mbar_expect_tx(n3_sr_full(c, slot), bytes);
+                tc::tma_bulk_g2s(c.ring0 + (size_t)slot * N3_BLOCK, weight_image + st.off, bytes, n3_sr_full(c, slot));
+                ++sr_it;
+            } else {
+                const uint32_t slot = st.it % N3_RING, round = st.it / N3_RING;
+                if (CL) {
+                    // rank 0 loads for both CTAs once BOTH have released the slot (EMPTY counts 2: my issuer's commit + the peer's multicast commit);
+                    // rank 1 only re-arms its own FULL barrier when its own issuer has released the slot (the bytes arrive from rank 0's multicast)
+                    if (round > 0) tc::mbar_wait(c.b + (c.crank ? B_LEMPTY : B_EMPTY) + slot, (round - 1) & 1);
+                    tc::mbar_expect_tx(c.b + B_FULL + slot, bytes);
+                    if (c.crank == 0) n3_tma_bulk_g2s_mc(c.ring + (size_t)slot * N3_BLOCK, weight_image + st.off, bytes, c.b + B_FULL + slot, (uint16_t)3);
+                } else if (!(c.dbg & 8)) {      // (bit3, only with bits 0|1: no ring handshake at all)
+                    if (round > 0) tc::mbar_wait(c.b + B_EMPTY + slot, (round - 1) & 1);
+                    if (c.dbg & 1) n3_arrive(c.b + B_FULL + slot);
+                    else { tc::mbar_expect_tx(c.b + B_FULL + slot, bytes); tc::tma_bulk_g2s(c.ring + (size_t)slot * N3_BLOCK, weight_image + st.off, bytes, c.b + B_FULL + slot); }
+                }
+                ++st.it;
             }
             st.off += bytes;
         }
         if (st.pending) {
-            // the K-block that last read AUX was issued one K-block ago: its ring slots have been released since, so its commit on AUXFREE (issued right
-            // behind the slot release) has landed or is about to — this wait does not stall the weight stream
-            if (st.pending != 3 || enc_next) {
-                tc::mbar_wait(c.b + B_AUXFREE, st.af & 1);
-                const uint8_t *src = st.pending == 1 ? enc + (size_t)aux_blocks * N3_BLOCK : st.pending == 2 ? enc + N3_BLOCK : enc_next;
-                uint64_t *eb = c.b + (st.pending == 1 ? B_E1 : st.pending == 2 ? B_E2 : B_E0);
-                tc::mbar_expect_tx(eb, N3_BLOCK);
-                tc::tma_bulk_g2s(c.A + N3_AUX * N3_BLOCK, src, N3_BLOCK, eb);
-            }
-            ++st.af;
+            // AUX refill. MD 0/1: one K-block after the one that last read AUX (its ring slots have been released since, so its commit on AUXFREE, issued right
+            // behind the slot release, has landed or is about to). MD 2: two K-blocks after it (4 slots): either way the wait does not stall the weight stream.
+            if (!SR || st.age == 1) {
+                if (st.pending != 3 || enc_next) {
+                    tc::mbar_wait(c.b + B_AUXFREE, st.af & 1);
+                    const uint8_t *src = st.pending == 1 ? enc + (size_t)aux_blocks * N3_BLOCK : st.pending == 2 ? enc + N3_BLOCK : enc_next;
+                    uint64_t *eb = c.b + (st.pending == 1 ? B_E1 : st.pending == 2 ? B_E2 : B_E0);
+                    tc::mbar_expect_tx(eb, N3_BLOCK);
+                    tc::tma_bulk_g2s(c.A + N3_AUX * N3_BLOCK, src, N3_BLOCK, eb);
+                }
+                ++st.af;
+                st.pending = 0;
+            } else st.age = 1;
         }
-        st.pending = (int)((RL >> (2 * kb)) & 3u);
+        if ((RL >> (2 * kb)) & 3u) { st.pending = (int)((RL >> (2 * kb)) & 3u); st.age = 0; }
     }
+    if (SR) c.busy[3] = sr_it;                             // the next producer in the global order may push
 }
-template <bool MIP, bool CL, int... LS>
+template <bool MIP, int MD, int... LS>
 __device__ __forceinline__ void n3_produce_tile(std::integer_sequence<int, LS...>, const N3Ctx &c, N3Prod &st, const uint8_t *__restrict__ weight_image, const uint8_t *enc, const uint8_t *enc_next) {
-    (n3_produce_layer<MIP, CL, LS>(c, st, weight_image, enc, enc_next), ...);
+    (n3_produce_layer<MIP, MD, LS>(c, st, weight_image, enc, enc_next), ...);
 }
 
 // ---------------------------------------------------------------------------------------------------- MMA issuer (whole warp walks, lane 0 issues)
@@ -157,11 +186,15 @@ __device__ __forceinline__ bool n3_elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
-template <bool MIP, bool CL, int LX>
+template <bool MIP, int MD, int LX>
 __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uint32_t tcount) {
     constexpr N3L L = n3_layer<MIP>(LX);
     constexpr uint32_t idesc = tc::idesc_f16_m128((uint32_t)L.N);
     constexpr uint32_t SRC = n3_pack(L.src, 3), WE = n3_pack(L.wait_enc, 2), RL = n3_pack(L.reload, 2);
+    constexpr bool CL = MD == 1, SR = MD == 2;
+    constexpr uint32_t cnt = (uint32_t)(L.n_kb * L.n_halves);
+    uint32_t sr_it = 0;
+    if (SR) { sr_it = it + (c.p ? cnt : 0u); it += 2 * cnt; }      // my slabs in the shared ring's global order: pipeline 0's slabs of this layer, then pipeline 1's
     tc::named_bar_sync(5 + c.p, 288);                             // the layer's input rows are in H, the previous accumulator is drained (hardware barrier)
     const bool tr = (c.dbg & 16) && blockIdx.x == 0 && tcount == 2;     // both pipelines' issuers are traced: events 0/1 (pipeline 0), 4/7 (pipeline 1)
     // Tensor-pipe turn taking. Left alone the two pipelines LOCK IN PHASE (timeline r01c: both issuers start every layer within ~20 cycles of each
@@ -177,9 +210,10 @@ __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uin
         if (c.p == 1 && n3_elect_one()) c.busy[1] = 1;
         __syncwarp();
     }
+    if (SR) { while (c.busy[2] != sr_it) {} }   // my turn: every earlier slab of the global order has been issued (and no parity wait can be two ring rounds ahead)
     if (tr && n3_elect_one()) n3_trace_buf[c.p ? 4 : 0][LX] = clock64();
     tc::tc_fence_after_sync();
-    const uint32_t a_lo = n3_desc_lo(tc::smem_u32(c.A)), b_lo = n3_desc_lo(tc::smem_u32(c.ring));
+    const uint32_t a_lo = n3_desc_lo(tc::smem_u32(c.A)), b_lo = n3_desc_lo(tc::smem_u32(SR ? c.ring0 : c.ring));
 #pragma unroll 1
     for (int kb = 0; kb < L.n_kb; ++kb) {
         const uint32_t we = (WE >> (2 * kb)) & 3u;
@@ -190,10 +224,12 @@ __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uin
         }
         const uint32_t a0 = a_lo + ((SRC >> (3 * kb)) & 7u) * (N3_BLOCK >> 4);
 #pragma unroll
-        for (int h = 0; h < L.n_halves; ++h, ++it) {
-            const uint32_t slot = it % N3_RING, round = it / N3_RING;
-            if (c.dbg & 8) continue;
-            tc::mbar_wait(c.b + B_FULL + slot, round & 1);
+        for (int h = 0; h < L.n_halves; ++h) {
+            const uint32_t slot = SR ? sr_it % 4u : it % N3_RING, round = SR ? sr_it / 4u : it / N3_RING;
+            if (SR) ++sr_it; else ++it;
+            uint64_t *full = SR ? n3_sr_full(c, slot) : c.b + B_FULL + slot, *empty = SR ? n3_sr_empty(c, slot) : c.b + B_EMPTY + slot;
+            if (!SR && (c.dbg & 8)) continue;
+            tc::mbar_wait(full, round & 1);
             tc::tc_fence_after_sync();
             const uint32_t b0 = b_lo + slot * (N3_BLOCK >> 4);
             if (n3_elect_one()) {
@@ -210,7 +246,7 @@ __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uin
                     }
                 }
                 if (CL && c.crank) { tc::mma_commit(c.b + B_LEMPTY + slot); n3_commit_mc(c.b + B_EMPTY + slot, (uint16_t)1); }   // my producer may re-arm; rank 0 may reload
-                else tc::mma_commit(c.b + B_EMPTY + slot);
+                else tc::mma_commit(empty);
             }
             __syncwarp();
         }
@@ -221,13 +257,14 @@ __device__ __forceinline__ void n3_issue_layer(const N3Ctx &c, uint32_t &it, uin
         if (L.commit_h3) tc::mma_commit(c.b + B_H3FREE);
         tc::mma_commit(c.b + B_ACC);                                  // accumulator of layer LX complete, H/AUX reads of the layer done
         c.busy[c.p] = 0;
+        if (SR) c.busy[2] = sr_it;                                    // the next consumer in the global order may start
         if (tr) n3_trace_buf[c.p ? 7 : 1][LX] = clock64();
     }
     __syncwarp();
 }
-template <bool MIP, bool CL, int... LS>
+template <bool MIP, int MD, int... LS>
 __device__ __forceinline__ void n3_issue_tile(std::integer_sequence<int, LS...>, const N3Ctx &c, uint32_t &it, uint32_t tcount) {
-    (n3_issue_layer<MIP, CL, LS>(c, it, tcount), ...);
+    (n3_issue_layer<MIP, MD, LS>(c, it, tcount), ...);
 }
 
 // ---------------------------------------------------------------------------------------------------- compute warpgroups
@@ -317,7 +354,7 @@ __device__ __forceinline__ void n3_epilogue_tile(std::integer_sequence<int, LS..
     (n3_epilogue_layer<MIP, LS>(c, s), ...);
 }
 
-template <bool MIP, bool CL>
+template <bool MIP, int MD>
 __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, int stagger, const uint8_t *__restrict__ weight_image, const float *__restrict__ bias_g, const uint8_t *__restrict__ enc_image,
                                                                       int64_t n_rows, float *__restrict__ raw) {
     extern __shared__ uint8_t dyn_smem[];
@@ -331,10 +368,10 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
     using Layers = std::make_integer_sequence<int, N3_LAYERS>;
 
     if (threadIdx.x == 0) {
-        busy[0] = 0; busy[1] = 0;
+        busy[0] = 0; busy[1] = 0; busy[2] = 0; busy[3] = 0;
         for (int p = 0; p < 2; ++p) {
             uint64_t *b = bars + p * B_PER_PIPE;
-            for (int s = 0; s < N3_RING; ++s) { tc::mbar_init(b + B_FULL + s, 1); tc::mbar_init(b + B_EMPTY + s, CL ? 2 : 1); tc::mbar_init(b + B_LEMPTY + s, 1); }
+            for (int s = 0; s < N3_RING; ++s) { tc::mbar_init(b + B_FULL + s, 1); tc::mbar_init(b + B_EMPTY + s, MD == 1 ? 2 : 1); tc::mbar_init(b + B_LEMPTY + s, 1); }
             tc::mbar_init(b + B_ACC, 1);
             tc::mbar_init(b + B_E0, 1); tc::mbar_init(b + B_E1, 1); tc::mbar_init(b + B_E2, 1); tc::mbar_init(b + B_E3, 1);
             tc::mbar_init(b + B_AUXFREE, 1); tc::mbar_init(b + B_H3FREE, 1);
@@ -344,7 +381,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
     if (warp == 16) tc::tmem_alloc<512>(tmem_slot);
     tc::tc_fence_before_sync();
     __syncthreads();
-    if (CL) n3_cluster_sync();                                   // the peer's barriers are initialised before anything of mine can signal them
+    if (MD == 1) n3_cluster_sync();                                   // the peer's barriers are initialised before anything of mine can signal them
     tc::tc_fence_after_sync();
     const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int64_t n_tiles = (n_rows + 127) / 128;
@@ -353,7 +390,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
     N3Ctx c;
     c.p = warp >= 16 ? (warp & 1) : (warp >> 3);                 // warps 16,18 / 0-7 -> pipeline 0; 17,19 / 8-15 -> pipeline 1
     c.b = bars + c.p * B_PER_PIPE; c.A = base + (size_t)c.p * N3_PIPE_A; c.ring = ring_base + (size_t)c.p * N3_RING * N3_BLOCK; c.dbg = dbg;
-    c.tmem_p = tmem + (uint32_t)c.p * 256u; c.busy = busy; c.crank = CL ? (int)n3_cluster_rank() : 0;
+    c.tmem_p = tmem + (uint32_t)c.p * 256u; c.busy = busy; c.crank = MD == 1 ? (int)n3_cluster_rank() : 0; c.bars0 = bars; c.ring0 = ring_base;
     // tile of (round r, CTA, pipeline p) = (r * gridDim.x + blockIdx.x) * 2 + p. EVERY pipeline of the grid walks the same number of rounds; a tile index
     // past the end is a PHANTOM tile: it is computed on the last tile's encodings and writes nothing. (The two CTAs of a pair must consume the multicast
     // weight stream in lock step, so neither may stop early; without clusters the phantom work is at most one tile per pipeline.)
@@ -367,11 +404,11 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
         // simply starts half a layer period late and the two alternate: one drains its accumulators while the other one's MMAs run.
         if (c.p == 1) { const long long t0 = clock64(); while (clock64() - t0 < (long long)stagger) {} }
         uint32_t it = 0, tcount = 0;
-        for (int64_t r = 0; r < rounds; ++r, ++tcount) n3_issue_tile<MIP, CL>(Layers{}, c, it, tcount);
+        for (int64_t r = 0; r < rounds; ++r, ++tcount) n3_issue_tile<MIP, MD>(Layers{}, c, it, tcount);
     } else if (warp >= 16) {
         // ===================================================== producer of pipeline p
         if (lane == 0) {
-            N3Prod st{0, 0, 0, 0};
+            N3Prod st{};
             uint32_t n = 0;
             for (int64_t r = 0; r < rounds; ++r, ++n) {
                 const int64_t tile = min(vcta + r * vstride, n_tiles - 1), tile_next = min(vcta + (r + 1) * vstride, n_tiles - 1);   // phantom tiles re-read the last tile's encodings
@@ -384,7 +421,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
                     tc::tma_bulk_g2s(c.A + 3 * N3_BLOCK, enc + N3_BLOCK, N3_BLOCK, c.b + B_E3);
                 }
                 st.off = 0; st.pending = 0;
-                n3_produce_tile<MIP, CL>(Layers{}, c, st, weight_image, enc, enc_next);
+                n3_produce_tile<MIP, MD>(Layers{}, c, st, weight_image, enc, enc_next);
             }
         }
     } else {
@@ -412,7 +449,7 @@ __global__ void __launch_bounds__(N3_THREADS, 1) nerf_mlp_tc3_kernel(int dbg, in
     }
     tc::tc_fence_before_sync();
     __syncthreads();
-    if (CL) n3_cluster_sync();                                   // nobody leaves while the peer may still signal one of its barriers
+    if (MD == 1) n3_cluster_sync();                                   // nobody leaves while the peer may still signal one of its barriers
     if (warp == 16) tc::tmem_dealloc<512>(tmem);
 }
 
@@ -436,7 +473,7 @@ int xrb_nerf_mlp_forward_v3(const void *weight_image, const float *bias, const v
     const bool mip = input_ch > 64;
     const int dbg = getenv("XRB_NM_DBG") ? atoi(getenv("XRB_NM_DBG")) : 0;   // attribution experiments: bit0 no weight TMA, bit1 no MMAs, bit2 no epilogue math, bit3 (with 0|1) no weight-ring handshake, bit4 timeline, bit5 tensor-pipe turn taking between the two issuers
     const int stagger = getenv("XRB_N3_STAGGER") ? atoi(getenv("XRB_N3_STAGGER")) : 0;   // cycles by which pipeline 1 trails pipeline 0 (see the kernel)
-    constexpr size_t smem = 1024 + 2 * (size_t)N3_PIPE_A + 2 * (size_t)N3_RING * N3_BLOCK + 256 * sizeof(float) + 8 * (2 * B_PER_PIPE) + 16;
+    constexpr size_t smem = 1024 + 2 * (size_t)N3_PIPE_A + 2 * (size_t)N3_RING * N3_BLOCK + 256 * sizeof(float) + 8 * (2 * B_PER_PIPE) + 32;
     static_assert(smem <= 232448, "v3 shared memory budget");
     int dev = 0, sms = NUM_SMS; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t n_tiles = (n_rows + 127) / 128, pairs = (n_tiles + 1) / 2;
@@ -453,19 +490,21 @@ int xrb_nerf_mlp_forward_v3(const void *weight_image, const float *bias, const v
         const uint8_t *wi = (const uint8_t *)weight_image, *ei = (const uint8_t *)enc_image;
         cudaError_t e;
         if (mip) {
-            cudaFuncSetAttribute(nerf_mlp_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            e = cudaLaunchKernelEx(&cfg, nerf_mlp_tc3_kernel<true, true>, dbg, stagger, wi, bias, ei, n_rows, raw);
+            cudaFuncSetAttribute(nerf_mlp_tc3_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaLaunchKernelEx(&cfg, nerf_mlp_tc3_kernel<true, 1>, dbg, stagger, wi, bias, ei, n_rows, raw);
         } else {
-            cudaFuncSetAttribute(nerf_mlp_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            e = cudaLaunchKernelEx(&cfg, nerf_mlp_tc3_kernel<false, true>, dbg, stagger, wi, bias, ei, n_rows, raw);
+            cudaFuncSetAttribute(nerf_mlp_tc3_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaLaunchKernelEx(&cfg, nerf_mlp_tc3_kernel<false, 1>, dbg, stagger, wi, bias, ei, n_rows, raw);
         }
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -100; }
-    } else if (mip) {
-        cudaFuncSetAttribute(nerf_mlp_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        nerf_mlp_tc3_kernel<true, false><<<grid, N3_THREADS, smem, (cudaStream_t)stream>>>(dbg, stagger, (const uint8_t *)weight_image, bias, (const uint8_t *)enc_image, n_rows, raw);
     } else {
-        cudaFuncSetAttribute(nerf_mlp_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        nerf_mlp_tc3_kernel<false, false><<<grid, N3_THREADS, smem, (cudaStream_t)stream>>>(dbg, stagger, (const uint8_t *)weight_image, bias, (const uint8_t *)enc_image, n_rows, raw);
+        const int shared_ring = getenv("XRB_N3_SHARED_RING") ? atoi(getenv("XRB_N3_SHARED_RING")) : 0;   // MD 2, see n3_produce_layer
+        auto launch = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<grid, N3_THREADS, smem, (cudaStream_t)stream>>>(dbg, stagger, (const uint8_t *)weight_image, bias, (const uint8_t *)enc_image, n_rows, raw);
+        };
+        if (mip) { if (shared_ring) launch(nerf_mlp_tc3_kernel<true, 2>); else launch(nerf_mlp_tc3_kernel<true, 0>); }
+        else { if (shared_ring) launch(nerf_mlp_tc3_kernel<false, 2>); else launch(nerf_mlp_tc3_kernel<false, 0>); }
     }
     return check_launch("nerf_mlp_forward_v3");
 }
