@@ -203,6 +203,7 @@ def test_nerf_mlp_v3_cta_pair_multicast_matches_single_cta(cfg, n_rows, monkeypa
     monkeypatch.setenv('XRB_NERF_MLP_V', '3')
     image, bias = mlp._packed()
     out = {}
+    monkeypatch.setenv('XRB_N3_SHARED_RING', '0')             # private 2-slot rings (MD 0) / CTA pairs (MD 1)
     for cl in ('0', '1'):
         monkeypatch.setenv('XRB_N3_CLUSTER', cl)
         out[cl] = nerf_mlp_forward(image, bias, emb, mlp.input_ch, mlp.input_ch_dirs, version=3).clone()

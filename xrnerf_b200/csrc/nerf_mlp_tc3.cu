@@ -498,7 +498,7 @@ int xrb_nerf_mlp_forward_v3(const void *weight_image, const float *bias, const v
         }
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return -100; }
     } else {
-        const int shared_ring = getenv("XRB_N3_SHARED_RING") ? atoi(getenv("XRB_N3_SHARED_RING")) : 0;   // MD 2, see n3_produce_layer
+        const int shared_ring = getenv("XRB_N3_SHARED_RING") ? atoi(getenv("XRB_N3_SHARED_RING")) : 1;   // MD 2, see n3_produce_layer
         auto launch = [&](auto kern) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             kern<<<grid, N3_THREADS, smem, (cudaStream_t)stream>>>(dbg, stagger, (const uint8_t *)weight_image, bias, (const uint8_t *)enc_image, n_rows, raw);
