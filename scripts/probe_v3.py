@@ -30,7 +30,7 @@ raw = torch.empty((rows, 4), device='cuda')
 packs = {2: pack_nerf_mlp_v2(mlp), 3: pack_nerf_mlp_v3(mlp)}
 only = os.environ.get('PROBE_ONLY')
 for v in ((3,) if os.environ.get('PROBE_V3_ONLY') else (3, 2)):
-    for dbg in ([int(only)] if only else [0, 1, 2, 4, 7, 15]):
+    for dbg in ([int(only)] if only else [0, 1, 2, 4, 7]):
         os.environ['XRB_NM_DBG'] = str(dbg)
         image, bias = packs[v]
         t = timeit(lambda: nerf_mlp_forward_tiles(image, bias, enc, rows, 63, 27, raw, version=v))
