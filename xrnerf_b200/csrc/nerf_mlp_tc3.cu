@@ -6,10 +6,11 @@
 //
 //   warps 0-15   four compute warpgroups WG(p, c): tile p, output-column half c. thread == row == TMEM lane. Per layer: tcgen05.ld 32 columns
 //                at a time, + bias (packed half2), ReLU, fp16, STS.128 into the tile's swizzled H blocks (the next layer's A operand);
-//   warps 16,17  producer of pipeline 0 / 1 (one lane): streams the layer weights as [<=128 x 64] fp16 half-slabs through a 2-slot ring and
+//   warps 16,17  producer of pipeline 0 / 1 (one lane): streams the layer weights as 16 KB slabs ([256 x 32] K-halves for the 256-wide layers) through the
+//                weight ring — by default ONE ring of 4 slots shared by both pipelines and consumed in the global order P0.layer, P1.layer, ... — and
 //                TMA-loads the tile's encoding blocks;
-//   warps 18,19  MMA issuer of pipeline 0 / 1 (one lane): per K-block and output half 4 x tcgen05.mma (M=128, N=128|16, K=16) into the
-//                pipeline's 256 TMEM columns; everything a layer reads is complete before its epilogue rewrites H (no in-place race).
+//   warps 18,19  MMA issuer of pipeline 0 / 1 (converged warp, one elected lane): per slab 2 x tcgen05.mma (M=128, N=256, K=16) (4 x N=128|16 for the
+//                last two layers) into the pipeline's 256 TMEM columns; everything a layer reads is complete before its epilogue rewrites H.
 // Synchronisation: compute -> issuer is a hardware named barrier (bar.arrive x256 / bar.sync x32); issuer -> compute is one mbarrier
 // (tcgen05.commit) polled by ONE thread per pipeline, fanned out by a named barrier; 6 polling threads per SM in total.
 //
