@@ -316,6 +316,45 @@ def run_ours(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
 
+    # ---- whole-image inference (SURVEY 8d C2 "full 640 000-ray images"): 800x800 spiral views rendered in pixel order, one call per image.
+    # Placed before the training arm so that it renders the same (initial) weights as the batch arms.
+    image_arm = None
+    if not args.no_image:
+        from xrnerf_b200 import synth as _synth
+        poses = _synth.spiral_poses_ngp(40)
+        n_views = 4
+        views = []
+        for v in range(n_views):
+            o_np, d_np = _synth.get_rays_ngp(poses[(rank * n_views + v * 7) % 40])
+            views.append((torch.from_numpy(o_np).to(dev), torch.from_numpy(d_np).to(dev)))
+        n_img = views[0][0].shape[0]
+        img_r = NgpRenderer(field, samples_per_ray_budget=BUDGET)
+        res = {}
+        for path in ('chain', 'fused'):
+            fn = (lambda o_, d_: img_r.render_fused(o_, d_, bf)) if path == 'fused' else (lambda o_, d_: img_r.render(o_, d_, bf))
+            for v in range(2):
+                fn(*views[v])
+            barrier()
+            i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            KI = 12
+            i0.record()
+            for i in range(KI):
+                out_i = fn(*views[i % n_views])
+            i1.record()
+            barrier()
+            im = torch.tensor([i0.elapsed_time(i1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(im, op=dist.ReduceOp.MAX)
+            ns_i = out_i[2]
+            spr = float((ns_i[:, 0] if ns_i.dim() == 2 else ns_i).float().mean().item())
+            ms_img = float(im.item()) / KI
+            img_bytes = n_img * spr * (512 if path == 'fused' else BYTES_PER_SAMPLE) + n_img * 44          # gather (+ coords/raw round trip on the chain path) + ray I/O
+            pk, _ = peaks()
+            res[path] = {'value': world * n_img * KI / (float(im.item()) * 1e-3), 'unit': 'rays/s', 'ms_per_image': ms_img, 'samples_per_ray_mean': spr,
+                         'roofline': {'bound': 'hbm', 'achieved': img_bytes / (ms_img * 1e-3) / 1e9, 'peak': pk, 'unit': 'GB/s', 'frac': img_bytes / (ms_img * 1e-3) / 1e9 / pk,
+                                      'algorithmic_bytes_per_image': img_bytes, 'note': 'whole call(s) of one image; gather served by L1/L2 (coherent rays)'}}
+        image_arm = dict(res, what='800x800 spiral views in pixel order (coherent rays), 640 000 rays per call, sequential calls on one stream; 4 distinct views cycled (61 MB of rays)')
+
     # ---- parity sample (N=1): this arm's render of the 4096 rays the CPU reference arm renders below, taken BEFORE the training arm updates the weights
     parity_gpu = {}
     if world == 1:
@@ -510,6 +549,7 @@ def run_ours(args):
             'paths': {'chain': chain, 'fused': fused},
             'cpu_baseline': {'value': cpu_rate, 'unit': 'rays/s', 'cores': cores, 'kind': kind, 'sample': sample},
             'parity': parity,
+            'image': image_arm,
             'train': train,
             'grid_update': grid_upd,
             'nerf': nerf,
@@ -528,6 +568,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-train', dest='no_train', action='store_true', help='skip the training arm')
     ap.add_argument('--no-nerf', dest='no_nerf', action='store_true', help='skip the vanilla-NeRF arm')
+    ap.add_argument('--no-image', dest='no_image', action='store_true', help='skip the whole-image inference arm')
     ap.add_argument('--no-grid', dest='no_grid', action='store_true', help='skip the occupancy-grid update arm')
     ap.add_argument('--no-mip', dest='no_mip', action='store_true', help='skip the Mip-NeRF arm')
     ap.add_argument('--path', default='auto', choices=['auto', 'chain', 'fused'], help='inference path of the headline/e2e numbers: 5-launch chain, single-launch fused kernel, or the faster of the two (both are always measured)')

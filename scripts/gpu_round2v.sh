@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 400 python bench.py --steps 30 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "rc=$?"
+tail -3 gpurun_out/bench.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench.json').read().strip().split('\n')[-1])
+print('headline %.1f e2e %.1f train %.1f nerf %.2f mip %.2f' % (d['value']/1e6, d['e2e']['value']/1e6, d['train']['value']/1e6, d['nerf']['value']/1e6, d['mip']['value']/1e6)); print('image', d['image'])
+PY
