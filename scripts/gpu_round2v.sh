@@ -5,5 +5,5 @@ tail -3 gpurun_out/bench.err
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench.json').read().strip().split('\n')[-1])
-print('headline %.1f e2e %.1f train %.1f nerf %.2f mip %.2f' % (d['value']/1e6, d['e2e']['value']/1e6, d['train']['value']/1e6, d['nerf']['value']/1e6, d['mip']['value']/1e6)); print('image', d['image'])
+print('headline %.1f e2e %.1f' % (d['value']/1e6, d['e2e']['value']/1e6)); print('nerf', d['nerf']); print('nerf_train', d['nerf_train']); print('mip', str(d['mip'])[:200]); print('grid', str(d['grid_update'])[:150]); print('image', str(d['image'])[:200])
 PY
