@@ -106,6 +106,15 @@ def main():
     out.update({'gen.pose': pose, 'gen.K': K, 'gen.rays_o': res['rays_o'], 'gen.rays_d': res['rays_d_flat'], 'gen.viewdirs': res['viewdirs'], 'gen.radii': res['radii'].reshape(-1, 1),
                 'gen.z_lin': zres['z_vals'], 'gen.z_lindisp': zlin['z_vals'], 'gen.u': uz, 'gen.z_perturbed': zper['z_vals'], 'gen.pts': ptsg['pts'],
                 'gen.ngp_rays_o': ro_h.reshape(-1, 3).astype(np.float32), 'gen.ngp_rays_d': rd_h.reshape(-1, 3).astype(np.float32)})
+    # --- losses / metrics of the train steps (networks/utils/metrics.py:3-16; nerf.py:71-92, hashnerf.py:32-52, mipnerf.py:45-74)
+    met = R.load('networks.utils.metrics')
+    lx = torch.rand(96, 3); ly = (lx + 0.25 * torch.randn(96, 3)).clamp(0, 1)
+    lxg = lx.clone().requires_grad_(True)
+    h5 = met.HuberLoss(lxg, ly, 0.1, 'sum') * 5
+    h5.backward()
+    mse = met.img2mse(lx, ly)
+    out.update({'loss.x': lx, 'loss.y': ly, 'loss.huber_sum': met.HuberLoss(lx, ly, 0.1, 'sum'), 'loss.huber_mean': met.HuberLoss(lx, ly, 0.1, 'mean'),
+                'loss.huber5_grad': lxg.grad, 'loss.mse': mse, 'loss.psnr': met.mse2psnr(mse)})
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'nerf_golden.npz'),
                         **{k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in out.items()})
     print('wrote nerf_golden.npz with', len(out), 'arrays')
