@@ -21,7 +21,10 @@ def HuberLoss(x, y, delta=0.1, reduction='sum'):
 
 
 def unfold_batching(x):
-    return x[0] if torch.is_tensor(x) and x.dim() > 0 and x.shape[0] == 1 else x
+    """networks/utils/batching.py:5-12: (bs, N_per_sampler, ...) -> (bs * N_per_sampler, ...); 1-D tensors and non-tensors pass through."""
+    if torch.is_tensor(x) and x.dim() > 1:
+        return x.reshape((-1,) + tuple(x.shape[2:]))     # == torch.cat([x[b] for b in range(bs)], 0)
+    return x
 
 
 def merge_ret(ret, fine_ret):
@@ -214,15 +217,18 @@ class HashNerfNetwork(NerfNetwork):
         return {'rgbs': rgbs, 'disps': [], 'gt_imgs': gt_imgs, 'elapsed_time': [a.elapsed_time(b) * 1e-3 for a, b in elapsed], 'psnr': [float(p.item()) for p in psnrs]}
 
     def test_step(self, data, **kwargs):
-        """hashnerf.py:95-111: one spiral pose per call."""
+        """hashnerf.py:95-111: one spiral pose per call; `data` already holds the pose's rays (rays_o, rays_d, src_shape, idx) from the test pipeline.
+        A dict with only `poses` is run through the installed val pipeline first."""
         data = {k: unfold_batching(v) for k, v in data.items()}
+        idx = data.get('idx', 0)
+        idx = int(idx.item()) if torch.is_tensor(idx) else int(idx)
         with torch.no_grad():
-            d = self.val_pipeline({'pose': data['poses'], 'idx': data.get('idx', 0)}) if 'poses' in data and self.val_pipeline is not None else data
+            d = data if 'rays_o' in data else self.val_pipeline({'pose': data['poses'], 'idx': idx})
             ret = self.batchify_forward(d, is_test=True)
         rgb, alpha = ret['rgb'], ret['alpha']
         if 'src_shape' in d:
             rgb, alpha = recover_shape(rgb, d['src_shape']), recover_shape(alpha, d['src_shape'])
-        return {'spiral_rgb': rgb, 'spiral_alpha': alpha, 'idx': data.get('idx', 0)}
+        return {'spiral_rgb': rgb, 'spiral_alpha': alpha, 'idx': idx}
 
     def train_step(self, data, optimizer, **kwargs):
         data = {k: unfold_batching(v) for k, v in data.items()}
