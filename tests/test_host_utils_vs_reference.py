@@ -47,3 +47,24 @@ def test_update_batch_rays_rule():
         smp.set_iter(14)
         smp.update_batch_rays(True)
         assert smp.n_rays_per_batch == n0 and smp.measured_batch_size.item() == measured
+
+
+def test_reference_nerf_mlp_checkpoints_load_into_registry_modules():
+    """SURVEY 8f-4 (checkpoint compatibility): the state_dict of the REFERENCE's own NerfMLP (NeRF and Mip-NeRF embedders) has exactly our keys and shapes and loads
+    with strict=True; the packed tcgen05 weight image is rebuilt from the loaded weights."""
+    from xrnerf_b200 import registry as R
+    from xrnerf_b200.nerf_mlp import pack_nerf_mlp_v3
+    mlpm = _ref('mlps.nerf_mlp'); _ref('embedders.base'); _ref('embedders.mipnerf_embedder')
+    cfgs = [dict(skips=[4], netdepth=8, netwidth=256, output_ch=5, use_viewdirs=True, netchunk=1024 * 32, embedder=dict(type='BaseEmbedder', i_embed=0, multires=10, multires_dirs=4)),
+            dict(skips=[4], netdepth=8, netwidth=256, use_viewdirs=True, netchunk=1024 * 32,
+                 embedder=dict(type='MipNerfEmbedder', min_deg_point=0, max_deg_point=16, min_deg_view=0, max_deg_view=4, use_viewdirs=True, append_identity=True))]
+    for cfg in cfgs:
+        torch.manual_seed(0)
+        ref = mlpm.NerfMLP(**{k: (dict(v) if isinstance(v, dict) else v) for k, v in cfg.items()})
+        ours = R.build_mlp(dict(cfg, type='NerfMLP'))
+        sd_ref, sd_ours = ref.state_dict(), ours.state_dict()
+        assert list(sd_ref) == list(sd_ours) and all(sd_ref[k].shape == sd_ours[k].shape for k in sd_ref)
+        assert (ref.input_ch, ref.input_ch_dirs) == (ours.input_ch, ours.input_ch_dirs)
+        ours.load_state_dict(sd_ref, strict=True)
+        image, bias = pack_nerf_mlp_v3(ours)
+        assert torch.equal(bias[:256], sd_ref['pts_linears.0.bias']) and image.numel() > 1_000_000
