@@ -50,8 +50,8 @@ def test_registry_names_and_state_dict_keys():
 @pytest.mark.skipif(not os.path.isdir('/root/reference/configs'), reason='reference configs only exist in the build container')
 def test_reference_config_files_load_unchanged():
     from xrnerf_b200 import registry as R
-    for p, t in [('configs/nerf/nerf_blender_base01.py', 'NerfNetwork'), ('configs/instant_ngp/nerf_blender_local01.py', 'HashNerfNetwork'),
-                 ('configs/mipnerf/mipnerf_blender.py', 'MipNerfNetwork'), ('configs/mipnerf/mipnerf_multiscale.py', 'MipNerfNetwork')]:
+    for p, t in [('configs/nerf/nerf_blender_base01.py', 'NerfNetwork'), ('configs/nerf/nerf_llff_base01.py', 'NerfNetwork'), ('configs/instant_ngp/nerf_blender_local01.py', 'HashNerfNetwork'),
+                 ('configs/mipnerf/mipnerf_blender.py', 'MipNerfNetwork'), ('configs/mipnerf/mipnerf_multiscale.py', 'MipNerfNetwork')]:   # every config of the three model families
         cfg = R.load_config(os.path.join('/root/reference', p), dataname='lego')
         assert 'lego' in cfg.work_dir or 'lego' in str(cfg.get('basedata_cfg', ''))
         net = R.build_network(cfg.model)
