@@ -45,6 +45,21 @@ def test_argument_validation_without_gpu():
     assert lib.xrb_tcnn_hashgrid_num_params(bad) == -1 and b'unsupported' in lib.xrb_last_error()
     assert lib.xrb_nerf_mlp_forward(None, None, None, 10, 50, 27, None, None) == -2
     assert lib.xrb_nerf_sample_pdf(None, None, None, None, None, 4, 300, 128, None, None, None) == -2
+    # entry points added in round 1, session 2: sizes / supported shapes / null pointers / alignment, all checked before any CUDA call
+    assert lib.xrb_nerf_mlp_forward_v3(None, None, None, -1, 63, 27, None, None) == -1
+    assert lib.xrb_nerf_mlp_forward_v3(None, None, None, 10, 60, 27, None, None) == -2 and b'(63,27) or (96,27)' in lib.xrb_last_error()
+    assert lib.xrb_nerf_mlp_forward_v3(None, None, None, 0, 63, 27, None, None) == 0                       # empty input is not an error
+    assert lib.xrb_nerf_mlp_forward_v3(None, None, None, 10, 63, 27, None, None) == -1 and b'null' in lib.xrb_last_error()
+    buf = (C.c_char * 64)()
+    a = C.addressof(buf)
+    odd = C.c_void_p(a + 4)                                                                                  # not 16-byte aligned
+    assert lib.xrb_nerf_mlp_forward_v3(odd, odd, odd, 10, 63, 27, odd, None) == -1 and b'aligned' in lib.xrb_last_error()
+    assert lib.xrb_mip_ipe_tiles_rays(None, None, None, None, None, 4, 8, 0, 30, 0, 4, None, None) == -1 and b'wider' in lib.xrb_last_error()   # 180 IPE columns do not fit two blocks
+    assert lib.xrb_mip_ipe_tiles_rays(None, None, None, None, None, 0, 8, 0, 16, 0, 4, None, None) == 0
+    assert lib.xrb_mip_ipe_tiles_rays(None, None, None, None, None, 4, 8, 0, 16, 0, 4, None, None) == -1
+    assert lib.xrb_adam_ema_step(None, None, None, None, None, 8, C.c_float(1e-2), C.c_float(.9), C.c_float(.99), C.c_float(1e-15), C.c_float(0), 1, C.c_float(1), None, C.c_float(1.5), None) == -1
+    assert lib.xrb_adam_ema_step(None, None, None, None, None, 0, C.c_float(1e-2), C.c_float(.9), C.c_float(.99), C.c_float(1e-15), C.c_float(0), 1, C.c_float(1), None, C.c_float(0.05), None) == 0
+    assert lib.xrb_nerf_enc_image_bytes(129, 63) == 2 * 2 * 16384 and lib.xrb_nerf_enc_image_bytes(129, 96) == 2 * 3 * 16384
 
 
 def test_no_cpu_fallback():
