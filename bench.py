@@ -468,7 +468,28 @@ def run_ours(args):
                     tpeak = float(json.load(fh)['bf16_tflops_sustained'])
             except Exception:
                 tpeak = 1400.0
-            nerf = {'value': rps, 'unit': 'rays/s', 'workload': 'vanilla NeRF hierarchical 64 coarse + 192 fine evaluations per ray (configs[2]), 32768-ray batches, inference',
+            # CPU baseline leg of this arm (rank 0, N=1): BASELINE configs[0] shape - 1024 rays x 64 samples, coarse network only - through the numpy oracle
+            # (embed -> 12-layer NerfMLP -> composite; multi-threaded BLAS on the box's host cores). Checker code, timed only.
+            nerf_cpu = None
+            if world == 1:
+                try:
+                    from oracle import nerf_oracle as NO
+                    sd = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
+                    o_c = dev_batches[0][0][:1024].cpu().numpy(); d_c = dev_batches[0][1][:1024].cpu().numpy()
+                    z_c = np.broadcast_to(np.linspace(2, 6, 64, dtype=np.float32), (1024, 64)).copy()
+                    best = None
+                    for _ in range(2):
+                        tc0 = time.perf_counter()
+                        pts_c = o_c[:, None] + d_c[:, None] * z_c[..., None]
+                        raw_c = NO.nerf_mlp(sd, NO.embed(pts_c, d_c), 63, 27, prefix='mlp.').reshape(1024, 64, 4)
+                        NO.nerf_render(raw_c, z_c, d_c, white_bkgd=True)
+                        dtc = time.perf_counter() - tc0
+                        best = dtc if best is None else min(best, dtc)
+                    nerf_cpu = {'value': 1024 / best, 'unit': 'rays/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                'sample': 'configs[0]: 1024 rays x 64 samples, coarse network only, numpy oracle (fp32, multi-threaded BLAS); best of 2'}
+                except Exception as e:
+                    nerf_cpu = {'error': repr(e)[:200]}
+            nerf = {'value': rps, 'unit': 'rays/s', 'cpu_baseline': nerf_cpu, 'workload': 'vanilla NeRF hierarchical 64 coarse + 192 fine evaluations per ray (configs[2]), 32768-ray batches, inference',
                     'ms_per_batch': float(nm.item()) / KN, 'roofline': {'bound': 'tensor', 'achieved': rps * flop_per_ray / 1e12 / world, 'peak': tpeak, 'unit': 'TFLOP/s',
                                                                          'frac': rps * flop_per_ray / 1e12 / world / tpeak, 'flop_per_ray': flop_per_ray,
                                                                          'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a multi-kernel step)'}}
