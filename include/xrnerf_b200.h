@@ -230,7 +230,7 @@ int xrb_nerf_mlp_forward(const void *weight_image, const float *bias, const floa
 /* v2 of the same kernel: two epilogue warpgroups per tile, phased MMA issue, double-buffered TMEM accumulators, half-slab weight stream
  * (image/bias from xrnerf_b200.nerf_mlp.pack_nerf_mlp_v2) */
 int xrb_nerf_mlp_forward_v2(const void *weight_image, const float *bias, const void *enc_image, int64_t n_rows, int input_ch, int input_ch_dirs, float *raw, void *stream);
-/* v3 of the same chain (csrc/nerf_mlp_tc3.cu): two 128-row tiles in flight per SM so the tensor core runs one tile's layer while the other tile's
+/* v3 of the same chain — NerfMLP.run_mlp, /root/reference/xrnerf/models/mlps/nerf_mlp.py:70-94 — (csrc/nerf_mlp_tc3.cu): two 128-row tiles in flight per SM so the tensor core runs one tile's layer while the other tile's
  * accumulators are drained. weight_image / bias from the matching host packer (xrnerf_b200.nerf_mlp.pack_nerf_mlp_v3: bias = fp32 vector + fp16 copy). */
 int xrb_nerf_mlp_forward_v3(const void *weight_image, const float *bias, const void *enc_image, int64_t n_rows, int input_ch, int input_ch_dirs, float *raw, void *stream);
 /* encoding tile image consumed by v2 (per 128-row tile: point-encoding block(s) then direction block, [128x64] fp16, UMMA K-major 128B swizzle):
@@ -248,7 +248,8 @@ int xrb_nerf_posenc_tiles_rays(const float *rays_o, const float *rays_d, const f
 int xrb_mip_embed(const float *z_vals, const float *rays_o, const float *rays_d, const float *radii, const float *viewdirs, int n_rays, int n_samples, int min_deg_point,
                   int max_deg_point, int min_deg_view, int max_deg_view, float *embedded, float *means_out, float *covs_out, void *stream);
 
-/* The same cast_rays + IPE + view-direction encoding written straight into the fp16 tile image xrb_nerf_mlp_forward_v2 consumes
+/* The same cast_rays + IPE + view-direction encoding (networks/utils/mip.py:66-129, embedders/mipnerf_embedder.py:43-99) written straight into the fp16 tile image
+ * xrb_nerf_mlp_forward_v2 / _v3 consume
  * (xrb_nerf_enc_image_bytes(N*S, 6*(max_deg_point-min_deg_point)) bytes): no fp32 `embedded` round trip. Values are the fp16 roundings of xrb_mip_embed's. */
 int xrb_mip_ipe_tiles_rays(const float *z_vals, const float *rays_o, const float *rays_d, const float *radii, const float *viewdirs, int64_t n_rays, int n_samples, int min_deg_point,
                            int max_deg_point, int min_deg_view, int max_deg_view, void *enc_image, void *stream);
