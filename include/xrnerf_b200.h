@@ -70,7 +70,8 @@ int xrb_rm_ema_grid_samples(const float *grid_tmp, int n_elements, float decay, 
 
 /* replaces update_bitfield_api (pybind_api.h:25-26; src/update_bitfield.cu:74-116). mean f32[>=1] (only [0] written);
  * bitfield u8[8*128^3/8]. Deterministic (fixed-order) mean. */
-int xrb_rm_update_bitfield(const float *grid, float *mean, uint8_t *bitfield, void *stream);
+size_t xrb_rm_update_bitfield_workspace(void);   /* bytes of device scratch (the per-block partial sums of the fixed-order mean) */
+int xrb_rm_update_bitfield(const float *grid, float *mean, uint8_t *bitfield, void *workspace, void *stream);
 
 /* replaces rays_sampler_api (pybind_api.h:28-42; src/ray_sampler.cu:118-200).
  * rays_o/rays_d f32[N,3]; bitfield u8[2097152]; coords_out f32[max_samples,7] (rows = pos_warped[3], dt_warped,
@@ -120,6 +121,21 @@ typedef struct {
     int color_hidden;        /* hidden layers of color_net, 1..4 */
 } xrb_ngp_config;
 
+/* The hash table as the kernels read it: the fp16 working copy in tcnn's layout (always) and, optionally, its CELL IMAGE — a
+ * gather-friendly copy of the first n_packed_levels levels in which every grid cell stores its 8 corner entries as one aligned 32-byte
+ * record, so that a sample reads ONE 256-bit word per level instead of 8 scattered 4-byte entries (same values, 8x fewer L1 lines).
+ * cell_image == NULL / n_packed_levels == 0: every level is gathered from the table. The image is produced from the fp16 table by
+ * xrb_ngp_build_cell_image (xrb_ngp_cell_image_bytes bytes, 32-byte aligned; levels 0..4 = 10.6 MB, ..5 = 27.6 MB, ..6 = 72.6 MB for the
+ * reference config) and must be rebuilt when the table changes. It replaces nothing in the reference: tcnn gathers 8 entries per level
+ * (call site /root/reference/xrnerf/models/mlps/hashnerf_mlp.py:60). */
+typedef struct {
+    const void *table_fp16;
+    const void *cell_image;
+    int n_packed_levels;
+} xrb_ngp_table;
+size_t xrb_ngp_cell_image_bytes(const xrb_ngp_config *cfg, int n_packed_levels);
+int xrb_ngp_build_cell_image(const xrb_ngp_config *cfg, const void *table_fp16, int n_packed_levels, void *cell_image, void *stream);
+
 /* number of scalars in the hash table / density net / colour net parameter vectors, and level offsets */
 int64_t xrb_tcnn_hashgrid_num_params(const xrb_ngp_config *cfg);
 int64_t xrb_tcnn_density_num_params(const xrb_ngp_config *cfg);
@@ -134,7 +150,7 @@ size_t xrb_ngp_weight_image_bytes(const xrb_ngp_config *cfg);
 int xrb_ngp_pack_weights(const xrb_ngp_config *cfg, const float *density_params, const float *color_params, void *image, void *stream);
 
 /* tcnn.Encoding(HashGrid).forward: x f32[n,3] in [0,1] -> enc fp16[n, n_levels*n_features] */
-int xrb_tcnn_hashgrid_forward(const xrb_ngp_config *cfg, const void *table_fp16, const float *x, int x_stride, int n, void *enc_fp16, void *stream);
+int xrb_tcnn_hashgrid_forward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const float *x, int x_stride, int n, void *enc_fp16, void *stream);
 /* tcnn.Encoding(SphericalHarmonics, degree 4).forward: dirs f32[n,3] in [0,1] -> fp16[n,16] */
 int xrb_tcnn_sh4_forward(const float *dirs, int dir_stride, int n, void *out_fp16, void *stream);
 /* tcnn.Network(FullyFusedMLP).forward, SIMT reference-grade implementation: x fp16[n,in_w] -> y fp16[n,16] */
@@ -143,16 +159,16 @@ int xrb_tcnn_mlp_forward(const void *params_fp16, const void *x_fp16, int n, int
 /* HashNerfMLP.run_mlp (hashnerf_mlp.py:55-79) fused: pts/dirs f32 rows (stride in floats, so `coords[:, :3]` /
  * `coords[:, 4:]` views of a [S,7] buffer work in place) -> raw f32[n,4] = (rgb3, density1).
  * impl: 0 = SIMT (CUDA cores), 1 = tcgen05 tensor-core tiles (weights from `weight_image`). */
-int xrb_ngp_mlp_forward(const xrb_ngp_config *cfg, const void *table_fp16, const void *density_fp16, const void *color_fp16,
+int xrb_ngp_mlp_forward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *density_fp16, const void *color_fp16,
                         const void *weight_image, const float *pts, int pts_stride, const float *dirs, int dirs_stride, int n,
                         float *raw, int impl, void *stream);
 /* HashNerfMLP.run_density (hashnerf_mlp.py:107-111): -> density f32[n] (raw, pre-activation) */
-int xrb_ngp_density_forward(const xrb_ngp_config *cfg, const void *table_fp16, const void *density_fp16, const void *weight_image,
+int xrb_ngp_density_forward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *density_fp16, const void *weight_image,
                             const float *pts, int pts_stride, int n, float *density, int impl, void *stream);
 
 /* Backward of run_mlp: dL/draw f32[n,4] -> fp32 gradients of the three parameter vectors (ACCUMULATED into the
  * outputs with atomics; caller zeroes them). */
-int xrb_ngp_mlp_backward(const xrb_ngp_config *cfg, const void *table_fp16, const void *density_fp16, const void *color_fp16,
+int xrb_ngp_mlp_backward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *density_fp16, const void *color_fp16,
                          const float *pts, int pts_stride, const float *dirs, int dirs_stride, const float *dl_draw, int n,
                          float *d_table, float *d_density, float *d_color, void *stream);
 
@@ -174,13 +190,15 @@ int xrb_adam_ema_step(float *param, void *param_fp16, const float *grad, float *
  * rays_o/rays_d f32[N,3]; rgb f32[N,3]; alpha f32[N]; numsteps i32[N,2] (count, base) is also produced;
  * counters i32[2] as in xrb_rm_rays_sampler (counters[1] = total samples marched).
  * workspace: xrb_ngp_render_workspace(N, max_samples) bytes.
+ * ev_before_field / ev_after_field: optional cudaEvent_t handles (NULL = none) recorded on `stream` right before / after the field
+ * kernel, so a caller can time the dominant kernel live inside its own timed region (no library-global state).
  * ---------------------------------------------------------------------------------------------- */
 size_t xrb_ngp_render_workspace(int n_rays, int max_samples);
-int xrb_ngp_render(const xrb_ngp_config *cfg, const void *table_fp16, const void *weight_image, const uint8_t *bitfield,
+int xrb_ngp_render(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *weight_image, const uint8_t *bitfield,
                    const float *rays_o, const float *rays_d, int n_rays, int max_samples, float aabb0, float aabb1,
                    float near_distance, float cone_angle, uint64_t seed, int64_t n_prior_calls, const float *bg3_host, int rgb_act,
                    int dens_act, float *rgb_out, float *alpha_out, int32_t *numsteps, int32_t *counters, void *workspace,
-                   void *stream);
+                   void *ev_before_field, void *ev_after_field, void *stream);
 
 /* Single-launch variant: march + hash encode + MLPs (tcgen05) + composite in ONE persistent warp-specialised kernel; no per-sample
  * buffer exists, so there is no max_samples / overflow case. Same arithmetic as xrb_ngp_render (sample positions bit-identical; the
@@ -188,13 +206,11 @@ int xrb_ngp_render(const xrb_ngp_config *cfg, const void *table_fp16, const void
  * aligned, ZEROED ONCE by the caller at allocation (the kernel leaves its scheduler words zero on exit); one workspace per stream.
  * n_samples_out i32[n_rays] (samples per ray) may be NULL. alpha_out f32[n_rays]. */
 size_t xrb_ngp_render_fused_workspace(void);
-int xrb_ngp_render_fused(const xrb_ngp_config *cfg, const void *table_fp16, const void *weight_image, const uint8_t *bitfield,
+int xrb_ngp_render_fused(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *weight_image, const uint8_t *bitfield,
                          const float *rays_o, const float *rays_d, int n_rays, float aabb0, float aabb1, float near_distance,
                          float cone_angle, uint64_t seed, int64_t n_prior_calls, const float *bg3_host, int rgb_act, int dens_act,
                          float *rgb_out, float *alpha_out, int32_t *n_samples_out, void *workspace, void *stream);
 
-/* measurement hook: cudaEvent_t handles recorded right before / after the field kernel inside xrb_ngp_render (NULL disables) */
-int xrb_ngp_render_set_profile_events(void *before_field, void *after_field);
 
 /* ------------------------------------------------------------------------------------------------
  * NeRF / Mip-NeRF composite + sampling kernels (pure-PyTorch in the reference)

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 40
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.xrb_abi_version() == 1 and lib.xrb_built_for_sm() == 100
+    assert lib.xrb_abi_version() == 2 and lib.xrb_built_for_sm() == 100
 
 
 def test_python_binding_covers_header():
@@ -60,6 +60,59 @@ def test_argument_validation_without_gpu():
     assert lib.xrb_adam_ema_step(None, None, None, None, None, 8, C.c_float(1e-2), C.c_float(.9), C.c_float(.99), C.c_float(1e-15), C.c_float(0), 1, C.c_float(1), None, C.c_float(1.5), None) == -1
     assert lib.xrb_adam_ema_step(None, None, None, None, None, 0, C.c_float(1e-2), C.c_float(.9), C.c_float(.99), C.c_float(1e-15), C.c_float(0), 1, C.c_float(1), None, C.c_float(0.05), None) == 0
     assert lib.xrb_nerf_enc_image_bytes(129, 63) == 2 * 2 * 16384 and lib.xrb_nerf_enc_image_bytes(129, 96) == 2 * 3 * 16384
+
+
+def test_strided_or_wrong_dtype_tensors_are_rejected():
+    """Round-1 W1: a Fortran-ordered rays_o (what `broadcast_to -> reshape -> astype` + torch.from_numpy gives) was handed to the kernels as a bare
+    data_ptr() and silently rendered different rays. Every dense-row pointer now goes through _C.ptr, which refuses non-contiguous / wrong-dtype
+    tensors with the library's bad-argument status; the high-level renderers copy strided rays instead of reinterpreting them."""
+    import numpy as np
+    import torch
+    from xrnerf_b200 import _C, synth
+    from xrnerf_b200.ngp import _rays
+    base = np.broadcast_to(np.arange(3, dtype=np.float32), (10, 10, 3)).reshape(-1, 3).astype(np.float32)      # the round-1 construction
+    t = torch.from_numpy(base)
+    if not t.is_contiguous():                                                                                   # numpy keeps the broadcast's 'K' order here
+        with pytest.raises(_C.XrbError, match='non-contiguous'):
+            _C.ptr(t)
+    f = torch.zeros(6, 3).t()                                                                                   # explicit strided view
+    assert not f.is_contiguous()
+    with pytest.raises(_C.XrbError, match='XRB_E_BADARG'):
+        _C.ptr(f)
+    with pytest.raises(_C.XrbError, match='expected torch.float32'):
+        _C.f32(torch.zeros(4, dtype=torch.float64))
+    with pytest.raises(_C.XrbError):
+        _C.rows(torch.zeros(4, 7)[:, ::2])                                                                      # inner stride 2: not a row view
+    p, stride = _C.rows(torch.zeros(5, 7)[:, 4:])                                                               # coords[:, 4:] is a legal row view
+    assert stride == 7
+    r = _rays(torch.zeros(3, 8).t()[:, :3])
+    assert r.is_contiguous() and r.shape == (8, 3)
+    with pytest.raises(_C.XrbError):
+        _rays(torch.zeros(8, 3, dtype=torch.float64))
+    o, d = synth.get_rays_ngp(synth.spiral_poses_ngp(40)[3], h=12, w=20)
+    assert o.flags['C_CONTIGUOUS'] and d.flags['C_CONTIGUOUS'] and o.strides == (12, 4)
+
+
+def test_cell_image_layout_and_validation_without_gpu():
+    from xrnerf_b200 import _C
+    lib = _C.lib
+    cfg = _C.NgpConfig(16, 2, 19, 16, 1.38191288, 64, 1, 2)
+    res = (C.c_uint32 * 16)()
+    assert lib.xrb_tcnn_hashgrid_layout(cfg, None, None, res) == 0
+    for n in range(0, 9):
+        assert lib.xrb_ngp_cell_image_bytes(cfg, n) == 32 * sum(int(r) ** 3 for r in list(res)[:n])           # one 32-byte record per grid cell
+    assert lib.xrb_ngp_cell_image_bytes(cfg, 6) == 32 * (16 ** 3 + 23 ** 3 + 31 ** 3 + 43 ** 3 + 59 ** 3 + 81 ** 3)
+    assert lib.xrb_ngp_build_cell_image(cfg, None, 0, None, None) == 0
+    assert lib.xrb_ngp_build_cell_image(cfg, None, 9, None, None) == -1
+    assert lib.xrb_ngp_build_cell_image(cfg, None, 5, None, None) == -1 and b'null' in lib.xrb_last_error()
+    buf = (C.c_char * 256)()
+    a = (C.addressof(buf) + 63) & ~63
+    tab = _C.NgpTable(a, a + 4, 6)                                                                              # cell image not 32-byte aligned
+    out = C.c_void_p(a)
+    assert lib.xrb_ngp_mlp_forward(cfg, tab, None, None, out, out, 3, out, 3, 4, out, 1, None) == -1 and b'cell image' in lib.xrb_last_error()
+    assert lib.xrb_ngp_mlp_forward(cfg, None, None, None, out, out, 3, out, 3, 4, out, 1, None) == -1
+    assert lib.xrb_rm_update_bitfield(out, out, out, None, None) == -1                                          # scratch is the caller's
+    assert lib.xrb_rm_update_bitfield_workspace() == 512 * 4
 
 
 def test_no_cpu_fallback():

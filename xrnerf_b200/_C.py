@@ -23,9 +23,15 @@ class NgpConfig(C.Structure):
                 ('per_level_scale', C.c_float), ('width', C.c_int), ('density_hidden', C.c_int), ('color_hidden', C.c_int)]
 
 
+class NgpTable(C.Structure):
+    """xrb_ngp_table: the fp16 hash table (tcnn layout) + its optional cell image (include/xrnerf_b200.h)"""
+    _fields_ = [('table_fp16', C.c_void_p), ('cell_image', C.c_void_p), ('n_packed_levels', C.c_int)]
+
+
 P = C.c_void_p
 _i, _f, _u64, _i64, _sz = C.c_int, C.c_float, C.c_uint64, C.c_int64, C.c_size_t
 _cfg = C.POINTER(NgpConfig)
+_tab = C.POINTER(NgpTable)
 
 _SIGS = {
     'xrb_abi_version': (C.c_int, []),
@@ -35,7 +41,8 @@ _SIGS = {
     'xrb_rm_mark_untrained_density_grid': (_i, [P, P, _i, _i, _i, _i, P, P]),
     'xrb_rm_splat_grid_samples': (_i, [P, P, _i, _i, P, P]),
     'xrb_rm_ema_grid_samples': (_i, [P, _i, _f, P, P]),
-    'xrb_rm_update_bitfield': (_i, [P, P, P, P]),
+    'xrb_rm_update_bitfield_workspace': (_sz, []),
+    'xrb_rm_update_bitfield': (_i, [P, P, P, P, P]),
     'xrb_rm_rays_sampler_workspace': (_sz, [_i]),
     'xrb_rm_rays_sampler': (_i, [P, P, P, P, P, P, _i, _i, _f, _f, _f, _f, _u64, _i64, P, P, P, P, P, P]),
     'xrb_rm_compacted_coord_workspace': (_sz, [_i]),
@@ -50,18 +57,19 @@ _SIGS = {
     'xrb_tcnn_cast_params': (_i, [P, P, _i64, P]),
     'xrb_ngp_weight_image_bytes': (_sz, [_cfg]),
     'xrb_ngp_pack_weights': (_i, [_cfg, P, P, P, P]),
-    'xrb_tcnn_hashgrid_forward': (_i, [_cfg, P, P, _i, _i, P, P]),
+    'xrb_ngp_cell_image_bytes': (_sz, [_cfg, _i]),
+    'xrb_ngp_build_cell_image': (_i, [_cfg, P, _i, P, P]),
+    'xrb_tcnn_hashgrid_forward': (_i, [_cfg, _tab, P, _i, _i, P, P]),
     'xrb_tcnn_sh4_forward': (_i, [P, _i, _i, P, P]),
     'xrb_tcnn_mlp_forward': (_i, [P, P, _i, _i, _i, _i, P, P]),
-    'xrb_ngp_mlp_forward': (_i, [_cfg, P, P, P, P, P, _i, P, _i, _i, P, _i, P]),
-    'xrb_ngp_density_forward': (_i, [_cfg, P, P, P, P, _i, _i, P, _i, P]),
-    'xrb_ngp_mlp_backward': (_i, [_cfg, P, P, P, P, _i, P, _i, P, _i, P, P, P, P]),
+    'xrb_ngp_mlp_forward': (_i, [_cfg, _tab, P, P, P, P, _i, P, _i, _i, P, _i, P]),
+    'xrb_ngp_density_forward': (_i, [_cfg, _tab, P, P, P, _i, _i, P, _i, P]),
+    'xrb_ngp_mlp_backward': (_i, [_cfg, _tab, P, P, P, _i, P, _i, P, _i, P, P, P, P]),
     'xrb_adam_step': (_i, [P, P, P, P, P, _i64, _f, _f, _f, _f, _f, _i, _f, P]),
     'xrb_adam_ema_step': (_i, [P, P, P, P, P, _i64, _f, _f, _f, _f, _f, _i, _f, P, _f, P]),
     'xrb_ngp_render_workspace': (_sz, [_i, _i]),
     'xrb_ngp_render_fused_workspace': (_sz, []),
-    'xrb_ngp_render_fused': (_i, [_cfg, P, P, P, P, P, _i, _f, _f, _f, _f, _u64, _i64, C.POINTER(C.c_float), _i, _i, P, P, P, P, P]),
-    'xrb_ngp_render_set_profile_events': (_i, [P, P]),
+    'xrb_ngp_render_fused': (_i, [_cfg, _tab, P, P, P, P, _i, _f, _f, _f, _f, _u64, _i64, C.POINTER(C.c_float), _i, _i, P, P, P, P, P]),
     'xrb_nerf_composite_forward': (_i, [P, P, P, _i, _i, _i, _i, _f, _f, _i, P, P, P, P, P]),
     'xrb_nerf_composite_backward': (_i, [P, P, P, P, _i, _i, _i, _i, _f, _f, _i, P, P]),
     'xrb_nerf_sample_pdf': (_i, [P, P, P, P, P, _i, _i, _i, P, P, P]),
@@ -78,7 +86,7 @@ _SIGS = {
     'xrb_mip_resample': (_i, [P, P, P, _i, _i, _f, P, P]),
     'xrb_nerf_get_rays': (_i, [C.POINTER(C.c_float), _i, _i, _f, _f, _f, _f, _i, P, _i64, P, P, P, P, P]),
     'xrb_nerf_zvals': (_i, [_i64, _i, _f, _f, _i, P, P, P]),
-    'xrb_ngp_render': (_i, [_cfg, P, P, P, P, P, _i, _i, _f, _f, _f, _f, _u64, _i64, C.POINTER(C.c_float), _i, _i, P, P, P, P, P, P]),
+    'xrb_ngp_render': (_i, [_cfg, _tab, P, P, P, P, _i, _i, _f, _f, _f, _f, _u64, _i64, C.POINTER(C.c_float), _i, _i, P, P, P, P, P, P, P, P]),
 }
 
 EXPORTS = sorted(_SIGS)  # every symbol the header declares and the library currently implements
@@ -86,6 +94,9 @@ for _name, (_res, _args) in _SIGS.items():
     _fn = getattr(lib, _name)
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+XRB_E_BADARG = -1
 
 
 class XrbError(RuntimeError):
@@ -97,9 +108,40 @@ def check(status, what=''):
         raise XrbError(f'{what} failed with status {status}: {lib.xrb_last_error().decode()}')
 
 
-def ptr(t):
-    """Device (or host) pointer of a tensor; None -> NULL."""
-    return None if t is None else C.c_void_p(t.data_ptr())
+def ptr(t, dtype=None):
+    """Device (or host) pointer of a DENSE tensor; None -> NULL.
+
+    The kernels index `base + i * row_width`: a strided view (e.g. a Fortran-ordered `rays_o` that `torch.from_numpy` made
+    from a `broadcast_to(...).reshape(...)` array) would be read as different data without any error, so it is rejected here
+    with the library's bad-argument status instead (the reference's Python wrappers assert contiguity the same way,
+    /root/reference/xrnerf/models/renders/hashnerf_render.py:76-96). Row-strided inputs go through `rows()`."""
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise XrbError(f'XRB_E_BADARG ({XRB_E_BADARG}): non-contiguous tensor (shape {tuple(t.shape)}, strides {tuple(t.stride())}) passed to a kernel that '
+                       'reads dense rows; call .contiguous() first')
+    if dtype is not None and t.dtype != dtype:
+        raise XrbError(f'XRB_E_BADARG ({XRB_E_BADARG}): expected {dtype}, got {t.dtype}')
+    return C.c_void_p(t.data_ptr())
+
+
+def f32(t):
+    return ptr(t, torch.float32)
+
+
+def i32(t):
+    return ptr(t, torch.int32)
+
+
+def u8(t):
+    return ptr(t, torch.uint8)
+
+
+def rows(t):
+    """(pointer, row stride in floats) of a [n, >=3] float32 view whose rows are dense but may be spaced (coords[:, :3], coords[:, 4:])."""
+    if t.dtype != torch.float32 or t.dim() != 2 or t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        raise XrbError(f'XRB_E_BADARG ({XRB_E_BADARG}): expected float32 rows with unit inner stride, got {t.dtype} shape {tuple(t.shape)} strides {tuple(t.stride())}')
+    return C.c_void_p(t.data_ptr()), int(t.stride(0))
 
 
 def stream():

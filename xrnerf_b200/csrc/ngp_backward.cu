@@ -91,7 +91,7 @@ __device__ __forceinline__ void stage_dy(__half *DY, const float *g, int n) {  /
 
 // DH/CH fixed by template so that the register accumulators have static shapes
 template <int DH, int CH>
-__global__ void __launch_bounds__(BW_THREADS) ngp_field_bwd_kernel(HashGridDev g, const __half2 *__restrict__ table, const __half *__restrict__ dens_p, const __half *__restrict__ color_p,
+__global__ void __launch_bounds__(BW_THREADS) ngp_field_bwd_kernel(HashGridDev g, const __half2 *__restrict__ table, const uint8_t *__restrict__ cells, const __half *__restrict__ dens_p, const __half *__restrict__ color_p,
                                                                    const float *__restrict__ pts, int pts_stride, const float *__restrict__ dirs, int dirs_stride,
                                                                    const float4 *__restrict__ dl_draw, int n, const int32_t *__restrict__ n_dev, float *__restrict__ d_table,
                                                                    float *__restrict__ d_dens, float *__restrict__ d_color) {
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(BW_THREADS) ngp_field_bwd_kernel(HashGridDev g
         {
             float enc[32];
 #pragma unroll
-            for (int l = 0; l < 16; ++l) { float2 f = hash_level(table, g, l, px, py, pz); enc[2 * l] = f.x; enc[2 * l + 1] = f.y; }
+            for (int l = 0; l < 16; ++l) { float2 f = hash_level(table, cells, g, l, px, py, pz); enc[2 * l] = f.x; enc[2 * l + 1] = f.y; }
             store_row_h(ENC + (size_t)threadIdx.x * 32, enc, 32);
         }
         float dout[16];
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(BW_THREADS) ngp_field_bwd_kernel(HashGridDev g
 }
 
 template <int DH, int CH>
-static int launch_bwd(const HashGridDev &g, const void *table, const void *dens, const void *color, const float *pts, int pts_stride, const float *dirs, int dirs_stride,
+static int launch_bwd(const HashGridDev &g, const void *table, const void *cells, const void *dens, const void *color, const float *pts, int pts_stride, const float *dirs, int dirs_stride,
                       const float *dl_draw, int n, const int32_t *n_dev, float *d_table, float *d_dens, float *d_color, cudaStream_t s) {
     constexpr int ND = 64 * 32 + (DH - 1) * 64 * 64 + 16 * 64, NC = 64 * 32 + (CH - 1) * 64 * 64 + 16 * 64;
     size_t smem = sizeof(__half) * ((size_t)ND + NC + 128 * 32 * 2 + (size_t)(DH + CH) * 128 * 64 + 128 * 64);
@@ -260,7 +260,7 @@ static int launch_bwd(const HashGridDev &g, const void *table, const void *dens,
     int per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, BW_THREADS, smem); if (per_sm < 1) per_sm = 1;
     int dev = 0, sms = NUM_SMS; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int n_tiles = (n + 127) / 128, grid = sms * per_sm; if (grid > n_tiles) grid = n_tiles; if (grid < 1) grid = 1;
-    k<<<grid, BW_THREADS, smem, s>>>(g, (const __half2 *)table, (const __half *)dens, (const __half *)color, pts, pts_stride, dirs, dirs_stride, (const float4 *)dl_draw, n, n_dev, d_table,
+    k<<<grid, BW_THREADS, smem, s>>>(g, (const __half2 *)table, (const uint8_t *)cells, (const __half *)dens, (const __half *)color, pts, pts_stride, dirs, dirs_stride, (const float4 *)dl_draw, n, n_dev, d_table,
                                      d_dens, d_color);
     return check_launch("ngp_mlp_backward");
 }
@@ -288,16 +288,16 @@ using namespace xrb;
 
 extern "C" {
 
-int xrb_ngp_mlp_backward(const xrb_ngp_config *cfg, const void *table_fp16, const void *density_fp16, const void *color_fp16, const float *pts, int pts_stride, const float *dirs,
+int xrb_ngp_mlp_backward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *density_fp16, const void *color_fp16, const float *pts, int pts_stride, const float *dirs,
                          int dirs_stride, const float *dl_draw, int n, float *d_table, float *d_density, float *d_color, void *stream) {
     int e = check_cfg(cfg); if (e) return e;
     XRB_REQUIRE(n >= 0 && pts_stride >= 3 && dirs_stride >= 3, "ngp_mlp_backward: bad size");
     if (n == 0) return XRB_OK;
-    XRB_REQUIRE(table_fp16 && density_fp16 && color_fp16 && pts && dirs && dl_draw && d_table && d_density && d_color, "ngp_mlp_backward: null pointer");
+    XRB_REQUIRE(table && density_fp16 && color_fp16 && pts && dirs && dl_draw && d_table && d_density && d_color, "ngp_mlp_backward: null pointer");
     XRB_REQUIRE(((uintptr_t)dl_draw & 15) == 0 && ((uintptr_t)d_table & 7) == 0, "ngp_mlp_backward: dl_draw must be 16-byte, d_table 8-byte aligned");
-    HashGridDev g; hashgrid_build(cfg, &g);
+    HashGridDev g; e = table_setup(cfg, table, &g, "ngp_mlp_backward"); if (e) return e;
     cudaStream_t s = (cudaStream_t)stream;
-#define XRB_BW(DH, CH) if (cfg->density_hidden == DH && cfg->color_hidden == CH) return launch_bwd<DH, CH>(g, table_fp16, density_fp16, color_fp16, pts, pts_stride, dirs, dirs_stride, dl_draw, n, nullptr, d_table, d_density, d_color, s);
+#define XRB_BW(DH, CH) if (cfg->density_hidden == DH && cfg->color_hidden == CH) return launch_bwd<DH, CH>(g, table->table_fp16, table->cell_image, density_fp16, color_fp16, pts, pts_stride, dirs, dirs_stride, dl_draw, n, nullptr, d_table, d_density, d_color, s);
     XRB_BW(1, 1) XRB_BW(1, 2) XRB_BW(2, 2) XRB_BW(1, 3) XRB_BW(2, 3)
 #undef XRB_BW
     set_error("ngp_mlp_backward: (density_hidden, color_hidden) must be one of (1,1) (1,2) (2,2) (1,3) (2,3)");

@@ -15,6 +15,8 @@ struct HashGridDev {
     uint32_t res[MAX_LEVELS];
     int n_levels;
     uint32_t hashed_mask;             // bit l: level l is hashed (its table is the 2^log2_hashmap_size cap), else dense
+    uint32_t packed_mask;             // bit l: level l is gathered from the CELL IMAGE (one 32-byte record per grid cell), see cell_image_build()
+    uint32_t cell_off[MAX_LEVELS];    // first record of level l inside the cell image (units: 32-byte records)
 };
 
 inline int64_t hashgrid_build(const xrb_ngp_config *cfg, HashGridDev *g) {
@@ -32,8 +34,25 @@ inline int64_t hashgrid_build(const xrb_ngp_config *cfg, HashGridDev *g) {
         g->offset[l] = off; g->scale[l] = scale; g->res[l] = res; off += p;
     }
     g->offset[cfg->n_levels] = off;
+    g->packed_mask = 0;
+    for (int l = 0; l < MAX_LEVELS; ++l) g->cell_off[l] = 0;
     return (int64_t)off * cfg->n_features;
 }
+// Cell image: a gather-friendly COPY of the first `n_packed` levels of the fp16 table. Level l stores, for every grid cell
+// (gx,gy,gz) in [0,res)^3, its 8 corner feature pairs as ONE aligned 32-byte record (corner c = bit0 x, bit1 y, bit2 z; the entry
+// tcnn's grid_index() addresses for that corner), cells in x-fastest order. A sample then reads one 256-bit word per level (one L1
+// wavefront / one sector) instead of 8 scattered 4-byte entries (up to 8 wavefronts / sectors). The master parameters keep tcnn's
+// layout (state_dict compatibility); the image is rebuilt from the fp16 table whenever that changes. Returns the image size in bytes
+// and fills packed_mask / cell_off.
+inline size_t cell_image_layout(HashGridDev *g, int n_packed) {
+    size_t rec = 0; g->packed_mask = 0;
+    for (int l = 0; l < g->n_levels && l < n_packed; ++l) {
+        g->cell_off[l] = (uint32_t)rec; g->packed_mask |= 1u << l;
+        rec += (size_t)g->res[l] * g->res[l] * g->res[l];
+    }
+    return rec * 32;
+}
+constexpr int MAX_PACKED_LEVELS = 8;   // level 7 (res 154) is 117 MB of records; beyond that the image outgrows any cache
 __host__ __device__ inline int64_t mlp_num_params(int in_w, int width, int n_hidden, int out_pad) { return (int64_t)width * in_w + (int64_t)(n_hidden - 1) * width * width + (int64_t)out_pad * width; }
 
 inline int check_cfg(const xrb_ngp_config *cfg) {
@@ -47,8 +66,9 @@ inline int check_cfg(const xrb_ngp_config *cfg) {
 }
 
 // defined in ngp_mlp.cu: launches the field (impl 0 CUDA cores / 1 tcgen05) on n rows; if n_dev != NULL the effective row
-// count is min(n, *n_dev) read on the device.
-int launch_field(const xrb_ngp_config *cfg, const void *table, const void *dens, const void *color, const void *image, const float *pts, int pts_stride, const float *dirs,
+// count is min(n, *n_dev) read on the device. table_setup validates an xrb_ngp_table and describes it for the device.
+int table_setup(const xrb_ngp_config *cfg, const xrb_ngp_table *t, HashGridDev *g, const char *who);
+int launch_field(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *dens, const void *color, const void *image, const float *pts, int pts_stride, const float *dirs,
                  int dirs_stride, int n, const int32_t *n_dev, float *out, int impl, bool density_only, cudaStream_t s);
 
 #ifdef __CUDACC__
@@ -67,15 +87,44 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t 
     return index >= hashmap_size ? index - hashmap_size : index;
 }
 
+// 256-bit / 64-bit read-only gathers (SASS: LDG.E.256.CONSTANT / LDG.E.64.CONSTANT)
+struct __align__(32) Cell32 { uint32_t v[8]; };
+__device__ __forceinline__ Cell32 ldg_cell(const void *p) {
+    Cell32 r;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
+
 // one level of the multiresolution hash encoding: returns the two interpolated features (fp32, NOT yet rounded).
 // Index arithmetic is tcnn's grid_index() strength-reduced without changing any value:
 //   hashed level (res^3 > table size == 2^log2_hashmap_size): (x ^ y*P1 ^ z*P2) & (size-1); the two products are shared by the 8 corners
 //   dense level: x + y*res + z*res^2 < 2*size -> one conditional subtract instead of `% size`
 // (the generic `%` compiled to ~130 predicated-off but ISSUED instructions per level: ncu r01d source view)
-__device__ __forceinline__ float2 hash_level(const __half2 *__restrict__ table, const HashGridDev &g, int l, float x, float y, float z) {
+// Three gather forms, all returning the same 8 entries (the L1 processes one 128-byte line per cycle per load instruction, and a warp's
+// 32 scattered 4-byte reads touch up to 32 lines: the number of load instructions x lines is what the field kernel is bound by):
+//   packed level   : ONE 256-bit load of the cell's record from the cell image (cells: see cell_image_layout)
+//   hashed level   : the x-prime of the hash is 1, so entries (gx, y, z) and (gx^1, y, z) are the two halves of one aligned 8-byte word:
+//                    4 x 64-bit loads fetch both x-corners when gx is even and the gx corner when it is odd; odd lanes add 4 predicated
+//                    32-bit loads for gx+1 (6 instead of 8 lines per lane on average)
+//   dense, unpacked: 8 x 32-bit loads (only when the cell image is not given)
+// MODE: the gather form of level l when the caller knows it at compile time (the field kernels are specialised on "the first NP levels
+// are packed, every other level is hashed", which removes two of the three code paths per unrolled level), GATHER_RUNTIME otherwise.
+enum { GATHER_RUNTIME = 0, GATHER_PACKED = 1, GATHER_HASHED = 2, GATHER_DENSE = 3 };
+// gather form of level l under the static plan NP (NP == 0: decided at run time from the masks)
+template <int NP> __host__ __device__ constexpr int plan_mode(int l) { return NP == 0 ? GATHER_RUNTIME : (l < NP ? GATHER_PACKED : GATHER_HASHED); }
+// the static plan NP is valid for a grid iff exactly the first NP levels are packed and all others are hashed
+inline bool plan_valid(const HashGridDev &g, int np) {
+    if (np <= 0 || np > g.n_levels) return false;
+    const uint32_t all = g.n_levels >= 32 ? 0xffffffffu : ((1u << g.n_levels) - 1u), packed = (1u << np) - 1u;
+    return g.packed_mask == packed && ((g.hashed_mask | packed) & all) == all;
+}
+
+// (MODE is an ordinary argument of a force-inlined function: after unrolling it is a constant and the dead forms disappear)
+__device__ __forceinline__ float2 hash_level(const __half2 *__restrict__ table, const uint8_t *__restrict__ cells, const HashGridDev &g, int l, float x, float y, float z,
+                                             const int MODE = GATHER_RUNTIME) {
     const uint32_t off = g.offset[l], hs = g.offset[l + 1] - off, res = g.res[l];
-    const __half2 *tl = table + off;
-    asm volatile("" : "+l"(tl));   // keep the level base in a register pair: each gather address is then ONE imad.wide (base + idx*4), not a 64-bit add chain
     const float sc = g.scale[l];
     float px = __fmaf_rn(sc, x, 0.5f), py = __fmaf_rn(sc, y, 0.5f), pz = __fmaf_rn(sc, z, 0.5f);
     int ix_, iy_, iz_;
@@ -83,15 +132,40 @@ __device__ __forceinline__ float2 hash_level(const __half2 *__restrict__ table, 
     const uint32_t gx = (uint32_t)ix_, gy = (uint32_t)iy_, gz = (uint32_t)iz_;
     fx = px - fx; fy = py - fy; fz = pz - fz;
     __half2 v[8];
-    if ((g.hashed_mask >> l) & 1u) {   // uniform per level
+    const bool is_packed = MODE == GATHER_PACKED || (MODE == GATHER_RUNTIME && ((g.packed_mask >> l) & 1u));
+    const bool is_hashed = MODE == GATHER_HASHED || (MODE == GATHER_RUNTIME && ((g.hashed_mask >> l) & 1u));
+    if (is_packed) {   // uniform per level
+        // inputs are warped positions in [0,1] (cell coordinates in [0,res-1]); the clamp only keeps out-of-contract inputs inside the image
+        const uint32_t rm1 = res - 1u, cx = min(gx, rm1), cy = min(gy, rm1), cz = min(gz, rm1);
+        const Cell32 r = ldg_cell(cells + ((size_t)(g.cell_off[l] + cx + res * (cy + res * cz)) << 5));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = as_h2(r.v[c]);
+    } else if (is_hashed) {   // uniform per level
+        const __half2 *tl = table + off;
+        asm volatile("" : "+l"(tl));   // keep the level base in a register pair: each gather address is then ONE imad.wide (base + idx*4), not a 64-bit add chain
         const uint32_t mask = hs - 1u;
         const uint32_t hy0 = gy * 2654435761u, hy1 = hy0 + 2654435761u, hz0 = gz * 805459861u, hz1 = hz0 + 805459861u;
         const uint32_t a00 = hy0 ^ hz0, a10 = hy1 ^ hz0, a01 = hy0 ^ hz1, a11 = hy1 ^ hz1, gx1 = gx + 1u;
-        v[0] = __ldg(tl + ((gx ^ a00) & mask)); v[1] = __ldg(tl + ((gx1 ^ a00) & mask));
-        v[2] = __ldg(tl + ((gx ^ a10) & mask)); v[3] = __ldg(tl + ((gx1 ^ a10) & mask));
-        v[4] = __ldg(tl + ((gx ^ a01) & mask)); v[5] = __ldg(tl + ((gx1 ^ a01) & mask));
-        v[6] = __ldg(tl + ((gx ^ a11) & mask)); v[7] = __ldg(tl + ((gx1 ^ a11) & mask));
+        const uint32_t i0 = (gx ^ a00) & mask, i1 = (gx ^ a10) & mask, i2 = (gx ^ a01) & mask, i3 = (gx ^ a11) & mask;
+        // level offsets are multiples of 8 entries and the table is 16-byte aligned: (tl + (i & ~1)) is 8-byte aligned
+        const uint2 w0 = __ldg(reinterpret_cast<const uint2 *>(tl + (i0 & ~1u))), w1 = __ldg(reinterpret_cast<const uint2 *>(tl + (i1 & ~1u))),
+                    w2 = __ldg(reinterpret_cast<const uint2 *>(tl + (i2 & ~1u))), w3 = __ldg(reinterpret_cast<const uint2 *>(tl + (i3 & ~1u)));
+        uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+        const bool odd = gx & 1u;
+        if (odd) {   // gx+1 carries out of the aligned pair: its entry is elsewhere
+            n0 = __ldg(reinterpret_cast<const uint32_t *>(tl + ((gx1 ^ a00) & mask))); n1 = __ldg(reinterpret_cast<const uint32_t *>(tl + ((gx1 ^ a10) & mask)));
+            n2 = __ldg(reinterpret_cast<const uint32_t *>(tl + ((gx1 ^ a01) & mask))); n3 = __ldg(reinterpret_cast<const uint32_t *>(tl + ((gx1 ^ a11) & mask)));
+        }
+        // entry of gx = half (i & 1) of the word; entry of gx^1 = the other half (== gx+1 when gx is even)
+        const uint32_t e0 = (i0 & 1u) ? w0.y : w0.x, o0 = (i0 & 1u) ? w0.x : w0.y, e1 = (i1 & 1u) ? w1.y : w1.x, o1 = (i1 & 1u) ? w1.x : w1.y;
+        const uint32_t e2 = (i2 & 1u) ? w2.y : w2.x, o2 = (i2 & 1u) ? w2.x : w2.y, e3 = (i3 & 1u) ? w3.y : w3.x, o3 = (i3 & 1u) ? w3.x : w3.y;
+        v[0] = as_h2(e0); v[1] = as_h2(odd ? n0 : o0);
+        v[2] = as_h2(e1); v[3] = as_h2(odd ? n1 : o1);
+        v[4] = as_h2(e2); v[5] = as_h2(odd ? n2 : o2);
+        v[6] = as_h2(e3); v[7] = as_h2(odd ? n3 : o3);
     } else {
+        const __half2 *tl = table + off;
+        asm volatile("" : "+l"(tl));
         const uint32_t sy = res, sz = res * res, b = gx + gy * sy + gz * sz;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {  // all 8 gathers are issued before any is consumed (8 independent loads in flight per level)

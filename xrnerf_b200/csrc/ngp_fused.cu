@@ -35,7 +35,7 @@ constexpr int FR_MAX_WG = 2;                             // field warpgroups per
 
 struct FusedParams {
     HashGridDev g;
-    const __half2 *table; const void *weight_image; uint32_t image_bytes; int density_hidden, color_hidden;
+    const __half2 *table; const uint8_t *cells; int np; const void *weight_image; uint32_t image_bytes; int density_hidden, color_hidden;
     const uint8_t *bitfield; const float *rays_o; const float *rays_d; int n_rays;
     float lo, hi, near_distance, cone; Pcg32 rng;
     float bg[3]; int rgb_act, dens_act;
@@ -267,10 +267,24 @@ __global__ void __launch_bounds__((4 * FR_N_WG + N_PROD) * 32, 3 - FR_N_WG) ngp_
                         if (P.dbg & 1) {
                             for (int l = 0; l < 16; ++l) *reinterpret_cast<uint32_t *>(rowp + 4 * l) = pack_h2(x, y);
                         } else {
+                            // two ROLLED loops (see the file header), each with ONE gather form when the static plan holds (P.np > 0)
+                            if (P.np > 0) {
 #pragma unroll 1
-                            for (int l = 0; l < 16; ++l) {
-                                const float2 f = hash_level(P.table, P.g, l, x, y, z);
-                                *reinterpret_cast<uint32_t *>(rowp + 4 * l) = pack_h2(f.x, f.y);
+                                for (int l = 0; l < P.np; ++l) {
+                                    const float2 f = hash_level(P.table, P.cells, P.g, l, x, y, z, GATHER_PACKED);
+                                    *reinterpret_cast<uint32_t *>(rowp + 4 * l) = pack_h2(f.x, f.y);
+                                }
+#pragma unroll 1
+                                for (int l = P.np; l < 16; ++l) {
+                                    const float2 f = hash_level(P.table, P.cells, P.g, l, x, y, z, GATHER_HASHED);
+                                    *reinterpret_cast<uint32_t *>(rowp + 4 * l) = pack_h2(f.x, f.y);
+                                }
+                            } else {
+#pragma unroll 1
+                                for (int l = 0; l < 16; ++l) {
+                                    const float2 f = hash_level(P.table, P.cells, P.g, l, x, y, z, GATHER_RUNTIME);
+                                    *reinterpret_cast<uint32_t *>(rowp + 4 * l) = pack_h2(f.x, f.y);
+                                }
                             }
                         }
                         __syncwarp();
@@ -352,17 +366,18 @@ size_t xrb_ngp_render_fused_workspace(void) {
     return 256 + (size_t)sms * FUSED_MAX_PROD_PER_SM * 32 * FR_TCAP * sizeof(float) + (size_t)sms * 2 * 128;
 }
 
-int xrb_ngp_render_fused(const xrb_ngp_config *cfg, const void *table_fp16, const void *weight_image, const uint8_t *bitfield, const float *rays_o, const float *rays_d, int n_rays,
+int xrb_ngp_render_fused(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *weight_image, const uint8_t *bitfield, const float *rays_o, const float *rays_d, int n_rays,
                          float aabb0, float aabb1, float near_distance, float cone_angle, uint64_t seed, int64_t n_prior_calls, const float *bg3_host, int rgb_act, int dens_act,
                          float *rgb_out, float *alpha_out, int32_t *n_samples_out, void *workspace, void *stream) {
     int e = check_cfg(cfg); if (e) return e;
     XRB_REQUIRE(n_rays >= 0, "ngp_render_fused: bad size");
     if (n_rays == 0) return XRB_OK;
-    XRB_REQUIRE(table_fp16 && weight_image && bitfield && rays_o && rays_d && bg3_host && rgb_out && alpha_out && workspace, "ngp_render_fused: null pointer");
+    XRB_REQUIRE(table && weight_image && bitfield && rays_o && rays_d && bg3_host && rgb_out && alpha_out && workspace, "ngp_render_fused: null pointer");
     XRB_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)weight_image & 15) == 0, "ngp_render_fused: workspace must be 256-byte aligned, weight image 16-byte aligned");
     FusedParams P;
-    hashgrid_build(cfg, &P.g);
-    P.table = (const __half2 *)table_fp16; P.weight_image = weight_image; P.image_bytes = weight_image_layout(cfg->density_hidden, cfg->color_hidden).total;
+    e = table_setup(cfg, table, &P.g, "ngp_render_fused"); if (e) return e;
+    P.table = (const __half2 *)table->table_fp16; P.cells = (const uint8_t *)table->cell_image; P.np = plan_valid(P.g, table->n_packed_levels) ? table->n_packed_levels : 0;
+    P.weight_image = weight_image; P.image_bytes = weight_image_layout(cfg->density_hidden, cfg->color_hidden).total;
     P.density_hidden = cfg->density_hidden; P.color_hidden = cfg->color_hidden;
     P.bitfield = bitfield; P.rays_o = rays_o; P.rays_d = rays_d; P.n_rays = n_rays;
     P.lo = aabb0; P.hi = aabb1; P.near_distance = near_distance; P.cone = cone_angle; P.rng = host_rng(seed, n_prior_calls);
@@ -377,15 +392,7 @@ int xrb_ngp_render_fused(const xrb_ngp_config *cfg, const void *table_fp16, cons
     do {                                                                                                                                               \
         auto k = ngp_render_fused_kernel<NWG, NP, NS>;                                                                                                 \
         const size_t smem = fused_smem_bytes<NWG, NP, NS>(P.image_bytes);                                                                              \
-        static bool attr_set = false;                                                                                                                  \
-        if (!attr_set) {                                                                                                                               \
-            cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                                           \
-            if (getenv("XRB_DEBUG")) {                                                                                                                 \
-                cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, k);                                                                                  \
-                fprintf(stderr, "[xrb] fused<%d,%d,%d>: smem=%zu regs=%d local=%zu\n", NWG, NP, NS, smem, fa.numRegs, fa.localSizeBytes);              \
-            }                                                                                                                                          \
-            attr_set = true;                                                                                                                           \
-        }                                                                                                                                              \
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   /* per call: the attribute is per device and per image size */ \
         int grid = sms * (3 - NWG); if (n_groups < grid) grid = (int)n_groups;                                                                         \
         k<<<grid, (4 * NWG + NP) * 32, smem, (cudaStream_t)stream>>>(P);                                                                               \
     } while (0)

@@ -45,15 +45,31 @@ __global__ void pack_weights_kernel(const float *__restrict__ dens, const float 
     }
 }
 
+// ---------------------------------------------------------------------------- cell image (ngp_field.cuh: cell_image_layout)
+// thread = (record, corner): copies the entry tcnn's grid_index() addresses for that corner; 32 consecutive threads write 128 consecutive bytes
+__global__ void __launch_bounds__(256) cell_image_build_kernel(HashGridDev g, const __half2 *__restrict__ table, uint32_t *__restrict__ image, int n_packed, uint64_t n_words) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_words; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t rec = (uint32_t)(t >> 3), c = (uint32_t)t & 7u;
+        int l = 0;
+#pragma unroll
+        for (int k = 1; k < MAX_PACKED_LEVELS; ++k) if (k < n_packed && rec >= g.cell_off[k]) l = k;
+        const uint32_t res = g.res[l], cell = rec - g.cell_off[l];
+        const uint32_t gx = cell % res, gy = (cell / res) % res, gz = cell / (res * res);
+        const uint32_t hs = g.offset[l + 1] - g.offset[l];
+        const uint32_t idx = grid_index(gx + (c & 1u), gy + ((c >> 1) & 1u), gz + ((c >> 2) & 1u), hs, res);
+        image[t] = reinterpret_cast<const uint32_t *>(table)[g.offset[l] + idx];
+    }
+}
+
 // ---------------------------------------------------------------------------- stand-alone encodings
-__global__ void __launch_bounds__(256) hashgrid_forward_kernel(HashGridDev g, const __half2 *__restrict__ table, const float *__restrict__ x, int x_stride, int n,
-                                                               __half2 *__restrict__ enc) {
+__global__ void __launch_bounds__(256) hashgrid_forward_kernel(HashGridDev g, const __half2 *__restrict__ table, const uint8_t *__restrict__ cells, const float *__restrict__ x,
+                                                               int x_stride, int n, __half2 *__restrict__ enc) {
     // thread = (sample, level): consecutive lanes take consecutive levels of the same sample -> 64-byte coalesced row writes
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t i = t >> 4; int l = (int)(t & 15);
     if (i >= n) return;
     const float *p = x + (size_t)i * x_stride;
-    float2 f = hash_level(table, g, l, p[0], p[1], p[2]);
+    float2 f = hash_level(table, cells, g, l, p[0], p[1], p[2]);
     enc[(size_t)i * 16 + l] = __floats2half2_rn(f.x, f.y);
 }
 __global__ void __launch_bounds__(256) sh4_forward_kernel(const float *__restrict__ dirs, int stride, int n, __half *__restrict__ out) {
@@ -94,7 +110,7 @@ __device__ __forceinline__ void simt_net(const __half *__restrict__ P, int n_hid
 }
 
 template <bool DENSITY_ONLY>
-__global__ void __launch_bounds__(128) ngp_field_simt_kernel(HashGridDev g, const __half2 *__restrict__ table, const __half *__restrict__ dens_p, const __half *__restrict__ color_p,
+__global__ void __launch_bounds__(128) ngp_field_simt_kernel(HashGridDev g, const __half2 *__restrict__ table, const uint8_t *__restrict__ cells, const __half *__restrict__ dens_p, const __half *__restrict__ color_p,
                                                              int density_hidden, int color_hidden, const float *__restrict__ pts, int pts_stride, const float *__restrict__ dirs,
                                                              int dirs_stride, int n, const int32_t *__restrict__ n_dev, float *__restrict__ out) {
     extern __shared__ __half s_w[];
@@ -107,7 +123,7 @@ __global__ void __launch_bounds__(128) ngp_field_simt_kernel(HashGridDev g, cons
         const float *p = pts + (size_t)i * pts_stride;
         float enc[32];
 #pragma unroll
-        for (int l = 0; l < 16; ++l) { float2 f = hash_level(table, g, l, p[0], p[1], p[2]); enc[2 * l] = round_h(f.x); enc[2 * l + 1] = round_h(f.y); }
+        for (int l = 0; l < 16; ++l) { float2 f = hash_level(table, cells, g, l, p[0], p[1], p[2]); enc[2 * l] = round_h(f.x); enc[2 * l + 1] = round_h(f.y); }
         float dout[16];
         simt_net(s_w, density_hidden, enc, dout);
         if (DENSITY_ONLY) { out[i] = dout[0]; continue; }
@@ -146,8 +162,9 @@ constexpr int TC_WG = 2;                 // warpgroups (= concurrent 128-sample 
 constexpr uint32_t TC_TMEM_COLS = 128;   // 64 fp32 accumulator columns per warpgroup
 
 // MAXREG: 128 -> 2 CTAs/SM (16 warps); 80 -> 3 CTAs/SM (24 warps, ~70 B of spills): the gather is latency-bound, occupancy wins
-template <bool DENSITY_ONLY, int MAXREG>
-__global__ void __maxnreg__(MAXREG) ngp_field_tc_kernel(HashGridDev g, const __half2 *__restrict__ table, const void *__restrict__ weight_image, uint32_t image_bytes,
+// NP: static gather plan (ngp_field.cuh plan_mode): 0 = per-level form decided at run time, >0 = levels [0,NP) from the cell image, the rest hashed
+template <bool DENSITY_ONLY, int MAXREG, int NP>
+__global__ void __maxnreg__(MAXREG) ngp_field_tc_kernel(HashGridDev g, const __half2 *__restrict__ table, const uint8_t *__restrict__ cells, const void *__restrict__ weight_image, uint32_t image_bytes,
                                                                       int density_hidden, int color_hidden, const float *__restrict__ pts, int pts_stride,
                                                                       const float *__restrict__ dirs, int dirs_stride, int n, const int32_t *__restrict__ n_dev, float *__restrict__ out) {
     extern __shared__ uint8_t dyn_smem[];
@@ -166,10 +183,10 @@ __global__ void __maxnreg__(MAXREG) ngp_field_tc_kernel(HashGridDev g, const __h
         }
         if (DENSITY_ONLY) {
             float dout[16];
-            tc_density(c, L, density_hidden, table, g, x, y, z, dout);
+            tc_density<NP>(c, L, density_hidden, table, cells, g, x, y, z, dout);
             if (valid) out[i] = dout[0];
         } else {
-            float4 raw = tc_field(c, L, density_hidden, color_hidden, table, g, x, y, z, dx, dy, dz);
+            float4 raw = tc_field<NP>(c, L, density_hidden, color_hidden, table, cells, g, x, y, z, dx, dy, dz);
             if (valid) reinterpret_cast<float4 *>(out)[i] = raw;
         }
     }
@@ -224,14 +241,53 @@ int xrb_ngp_pack_weights(const xrb_ngp_config *cfg, const float *density_params,
     return check_launch("pack_weights");
 }
 
-int xrb_tcnn_hashgrid_forward(const xrb_ngp_config *cfg, const void *table_fp16, const float *x, int x_stride, int n, void *enc_fp16, void *stream) {
+size_t xrb_ngp_cell_image_bytes(const xrb_ngp_config *cfg, int n_packed_levels) {
+    if (check_cfg(cfg) || n_packed_levels <= 0) return 0;
+    if (n_packed_levels > MAX_PACKED_LEVELS) n_packed_levels = MAX_PACKED_LEVELS;
+    HashGridDev g; hashgrid_build(cfg, &g);
+    return cell_image_layout(&g, n_packed_levels);
+}
+
+int xrb_ngp_build_cell_image(const xrb_ngp_config *cfg, const void *table_fp16, int n_packed_levels, void *cell_image, void *stream) {
+    int e = check_cfg(cfg); if (e) return e;
+    XRB_REQUIRE(n_packed_levels >= 0 && n_packed_levels <= MAX_PACKED_LEVELS, "build_cell_image: n_packed_levels must be 0..8");
+    if (n_packed_levels == 0) return XRB_OK;
+    XRB_REQUIRE(table_fp16 && cell_image, "build_cell_image: null pointer");
+    XRB_REQUIRE(((uintptr_t)cell_image & 31) == 0 && ((uintptr_t)table_fp16 & 15) == 0, "build_cell_image: cell image must be 32-byte, table 16-byte aligned");
+    HashGridDev g; hashgrid_build(cfg, &g);
+    const uint64_t n_words = cell_image_layout(&g, n_packed_levels) / 4;
+    uint64_t blocks = (n_words + 255) / 256; if (blocks > (uint64_t)NUM_SMS * 32) blocks = (uint64_t)NUM_SMS * 32;
+    cell_image_build_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, (const __half2 *)table_fp16, (uint32_t *)cell_image, n_packed_levels, n_words);
+    return check_launch("build_cell_image");
+}
+
+}  // extern "C"
+namespace xrb {
+// validates an xrb_ngp_table and fills the device-side grid description (incl. the cell-image layout)
+int table_setup(const xrb_ngp_config *cfg, const xrb_ngp_table *t, HashGridDev *g, const char *who) {
+    if (!t || !t->table_fp16) { set_error("null hash table"); return XRB_E_BADARG; }
+    if (((uintptr_t)t->table_fp16 & 15) != 0) { set_error("hash table must be 16-byte aligned"); return XRB_E_BADARG; }
+    hashgrid_build(cfg, g);
+    if (t->n_packed_levels < 0 || t->n_packed_levels > MAX_PACKED_LEVELS) { set_error("n_packed_levels must be 0..8"); return XRB_E_BADARG; }
+    if (t->n_packed_levels > 0) {
+        if (!t->cell_image || ((uintptr_t)t->cell_image & 31) != 0) { set_error("cell image missing or not 32-byte aligned"); return XRB_E_BADARG; }
+        cell_image_layout(g, t->n_packed_levels);
+    }
+    (void)who;
+    return XRB_OK;
+}
+}  // namespace xrb
+extern "C" {
+
+int xrb_tcnn_hashgrid_forward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const float *x, int x_stride, int n, void *enc_fp16, void *stream) {
     int e = check_cfg(cfg); if (e) return e;
     XRB_REQUIRE(n >= 0 && x_stride >= 3, "hashgrid_forward: bad size");
     if (n == 0) return XRB_OK;
-    XRB_REQUIRE(table_fp16 && x && enc_fp16, "hashgrid_forward: null pointer");
-    HashGridDev g; hashgrid_build(cfg, &g);
+    XRB_REQUIRE(table && x && enc_fp16, "hashgrid_forward: null pointer");
+    HashGridDev g; e = table_setup(cfg, table, &g, "hashgrid_forward"); if (e) return e;
     int64_t threads = (int64_t)n * 16;
-    hashgrid_forward_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, (const __half2 *)table_fp16, x, x_stride, n, (__half2 *)enc_fp16);
+    hashgrid_forward_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, (const __half2 *)table->table_fp16, (const uint8_t *)table->cell_image, x, x_stride, n,
+                                                                                                 (__half2 *)enc_fp16);
     return check_launch("hashgrid_forward");
 }
 
@@ -257,37 +313,45 @@ int xrb_tcnn_mlp_forward(const void *params_fp16, const void *x_fp16, int n, int
 
 }  // extern "C"
 namespace xrb {
-int launch_field(const xrb_ngp_config *cfg, const void *table, const void *dens, const void *color, const void *image, const float *pts, int pts_stride, const float *dirs,
+int launch_field(const xrb_ngp_config *cfg, const xrb_ngp_table *tab, const void *dens, const void *color, const void *image, const float *pts, int pts_stride, const float *dirs,
                  int dirs_stride, int n, const int32_t *n_dev, float *out, int impl, bool density_only, cudaStream_t s) {
-    HashGridDev g; hashgrid_build(cfg, &g);
+    HashGridDev g; int e = table_setup(cfg, tab, &g, "field"); if (e) return e;
+    const void *table = tab->table_fp16; const uint8_t *cells = (const uint8_t *)tab->cell_image;
     if (impl == 0) {
         size_t smem = (mlp_num_params(32, 64, cfg->density_hidden, 16) + (density_only ? 0 : mlp_num_params(32, 64, cfg->color_hidden, 16))) * sizeof(__half);
         const void *k = density_only ? (const void *)ngp_field_simt_kernel<true> : (const void *)ngp_field_simt_kernel<false>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int grid = persistent_grid(k, 128, smem, (n + 127) / 128);
         if (density_only)
-            ngp_field_simt_kernel<true><<<grid, 128, smem, s>>>(g, (const __half2 *)table, (const __half *)dens, (const __half *)color, cfg->density_hidden, cfg->color_hidden, pts, pts_stride,
+            ngp_field_simt_kernel<true><<<grid, 128, smem, s>>>(g, (const __half2 *)table, cells, (const __half *)dens, (const __half *)color, cfg->density_hidden, cfg->color_hidden, pts, pts_stride,
                                                                 dirs, dirs_stride, n, n_dev, out);
         else
-            ngp_field_simt_kernel<false><<<grid, 128, smem, s>>>(g, (const __half2 *)table, (const __half *)dens, (const __half *)color, cfg->density_hidden, cfg->color_hidden, pts, pts_stride,
+            ngp_field_simt_kernel<false><<<grid, 128, smem, s>>>(g, (const __half2 *)table, cells, (const __half *)dens, (const __half *)color, cfg->density_hidden, cfg->color_hidden, pts, pts_stride,
                                                                  dirs, dirs_stride, n, n_dev, out);
     } else {
         uint32_t image_bytes = weight_image_layout(cfg->density_hidden, cfg->color_hidden).total;
         size_t smem = tc_cta_smem_bytes<TC_WG>(image_bytes);
         // register budget of the field kernel: 128 -> 2 CTAs/SM using the whole register file; 96 -> 2 CTAs/SM leaving 16K registers per SM
-        // for the (latency-bound, 36-register) march kernel of the NEXT batch to co-reside on another stream; 80 -> 3 CTAs/SM.
+        // for the (latency-bound, 36-register) march kernel of the NEXT batch to co-reside on another stream.
         static const int variant = getenv("XRB_TC_REGS") ? atoi(getenv("XRB_TC_REGS")) : 96;
-        const int regs = variant == 128 ? 128 : (variant == 80 ? 80 : 96);
+        const int regs = variant == 128 ? 128 : 96;
+        // static gather plan: the kernel is specialised for "levels [0,NP) packed, all others hashed" (NP = 5, 6, 7); anything else takes the run-time form
+        const int np = (plan_valid(g, tab->n_packed_levels) && tab->n_packed_levels >= 5 && tab->n_packed_levels <= 7) ? tab->n_packed_levels : 0;
         int n_tiles = (n + 127) / 128;
-#define XRB_LAUNCH_TC(D, R)                                                                                                                         \
+#define XRB_LAUNCH_TC(D, R, NP)                                                                                                                     \
     do {                                                                                                                                            \
-        auto k = ngp_field_tc_kernel<D, R>;                                                                                                         \
+        auto k = ngp_field_tc_kernel<D, R, NP>;                                                                                                     \
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                                            \
-        int grid = persistent_grid((const void *)k, 128 * TC_WG, smem, (n_tiles + TC_WG - 1) / TC_WG, R == 80 ? 3 : 2);                             \
-        k<<<grid, 128 * TC_WG, smem, s>>>(g, (const __half2 *)table, image, image_bytes, cfg->density_hidden, cfg->color_hidden, pts, pts_stride, dirs, dirs_stride, n, n_dev, out); \
+        int grid = persistent_grid((const void *)k, 128 * TC_WG, smem, (n_tiles + TC_WG - 1) / TC_WG, 2);                                           \
+        k<<<grid, 128 * TC_WG, smem, s>>>(g, (const __half2 *)table, cells, image, image_bytes, cfg->density_hidden, cfg->color_hidden, pts, pts_stride, dirs, dirs_stride, n, n_dev, out); \
     } while (0)
-        if (density_only) { if (regs == 128) XRB_LAUNCH_TC(true, 128); else if (regs == 96) XRB_LAUNCH_TC(true, 96); else XRB_LAUNCH_TC(true, 80); }
-        else { if (regs == 128) XRB_LAUNCH_TC(false, 128); else if (regs == 96) XRB_LAUNCH_TC(false, 96); else XRB_LAUNCH_TC(false, 80); }
+#define XRB_LAUNCH_TC_NP(D, R)                                                                                                                      \
+    do {                                                                                                                                            \
+        if (np == 5) XRB_LAUNCH_TC(D, R, 5); else if (np == 6) XRB_LAUNCH_TC(D, R, 6); else if (np == 7) XRB_LAUNCH_TC(D, R, 7); else XRB_LAUNCH_TC(D, R, 0); \
+    } while (0)
+        if (density_only) { if (regs == 128) XRB_LAUNCH_TC_NP(true, 128); else XRB_LAUNCH_TC_NP(true, 96); }
+        else { if (regs == 128) XRB_LAUNCH_TC_NP(false, 128); else XRB_LAUNCH_TC_NP(false, 96); }
+#undef XRB_LAUNCH_TC_NP
 #undef XRB_LAUNCH_TC
     }
     return check_launch(density_only ? "ngp_density_forward" : "ngp_mlp_forward");
@@ -295,25 +359,25 @@ int launch_field(const xrb_ngp_config *cfg, const void *table, const void *dens,
 }  // namespace xrb
 extern "C" {
 
-int xrb_ngp_mlp_forward(const xrb_ngp_config *cfg, const void *table_fp16, const void *density_fp16, const void *color_fp16, const void *weight_image, const float *pts, int pts_stride,
+int xrb_ngp_mlp_forward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *density_fp16, const void *color_fp16, const void *weight_image, const float *pts, int pts_stride,
                         const float *dirs, int dirs_stride, int n, float *raw, int impl, void *stream) {
     int e = check_cfg(cfg); if (e) return e;
     XRB_REQUIRE(n >= 0 && pts_stride >= 3 && dirs_stride >= 3, "ngp_mlp_forward: bad size");
     if (n == 0) return XRB_OK;
-    XRB_REQUIRE(table_fp16 && pts && dirs && raw, "ngp_mlp_forward: null pointer");
+    XRB_REQUIRE(table && pts && dirs && raw, "ngp_mlp_forward: null pointer");
     XRB_REQUIRE(((uintptr_t)raw & 15) == 0, "ngp_mlp_forward: raw must be 16-byte aligned");
     XRB_REQUIRE(impl == 0 ? (density_fp16 && color_fp16) : (weight_image != nullptr), "ngp_mlp_forward: missing weights for the requested impl");
-    return launch_field(cfg, table_fp16, density_fp16, color_fp16, weight_image, pts, pts_stride, dirs, dirs_stride, n, nullptr, raw, impl, false, (cudaStream_t)stream);
+    return launch_field(cfg, table, density_fp16, color_fp16, weight_image, pts, pts_stride, dirs, dirs_stride, n, nullptr, raw, impl, false, (cudaStream_t)stream);
 }
 
-int xrb_ngp_density_forward(const xrb_ngp_config *cfg, const void *table_fp16, const void *density_fp16, const void *weight_image, const float *pts, int pts_stride, int n, float *density,
+int xrb_ngp_density_forward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *density_fp16, const void *weight_image, const float *pts, int pts_stride, int n, float *density,
                             int impl, void *stream) {
     int e = check_cfg(cfg); if (e) return e;
     XRB_REQUIRE(n >= 0 && pts_stride >= 3, "ngp_density_forward: bad size");
     if (n == 0) return XRB_OK;
-    XRB_REQUIRE(table_fp16 && pts && density, "ngp_density_forward: null pointer");
+    XRB_REQUIRE(table && pts && density, "ngp_density_forward: null pointer");
     XRB_REQUIRE(impl == 0 ? (density_fp16 != nullptr) : (weight_image != nullptr), "ngp_density_forward: missing weights for the requested impl");
-    return launch_field(cfg, table_fp16, density_fp16, nullptr, weight_image, pts, pts_stride, nullptr, 3, n, nullptr, density, impl, true, (cudaStream_t)stream);
+    return launch_field(cfg, table, density_fp16, nullptr, weight_image, pts, pts_stride, nullptr, 3, n, nullptr, density, impl, true, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -6,26 +6,20 @@
 // the single-launch variant is tracked in DESIGN.md §6.
 #include "ngp_field.cuh"
 
-static thread_local cudaEvent_t g_ev_field0 = nullptr, g_ev_field1 = nullptr;
-
 extern "C" {
-
-// Measurement hook: when set (non-NULL cudaEvent_t handles), xrb_ngp_render records them on its stream immediately before and
-// after the field kernel launch, so a caller can time the dominant kernel live inside its own timed region (bench.py roofline).
-int xrb_ngp_render_set_profile_events(void *before_field, void *after_field) { g_ev_field0 = (cudaEvent_t)before_field; g_ev_field1 = (cudaEvent_t)after_field; return XRB_OK; }
 
 size_t xrb_ngp_render_workspace(int n_rays, int max_samples) {
     size_t a = (xrb_rm_rays_sampler_workspace(n_rays) + 255) & ~(size_t)255;
     return a + (size_t)max_samples * (7 + 4) * sizeof(float) + (size_t)n_rays * sizeof(int32_t) + 256;
 }
 
-int xrb_ngp_render(const xrb_ngp_config *cfg, const void *table_fp16, const void *weight_image, const uint8_t *bitfield, const float *rays_o, const float *rays_d, int n_rays,
+int xrb_ngp_render(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *weight_image, const uint8_t *bitfield, const float *rays_o, const float *rays_d, int n_rays,
                    int max_samples, float aabb0, float aabb1, float near_distance, float cone_angle, uint64_t seed, int64_t n_prior_calls, const float *bg3_host, int rgb_act,
-                   int dens_act, float *rgb_out, float *alpha_out, int32_t *numsteps, int32_t *counters, void *workspace, void *stream) {
+                   int dens_act, float *rgb_out, float *alpha_out, int32_t *numsteps, int32_t *counters, void *workspace, void *ev_before_field, void *ev_after_field, void *stream) {
     int e = xrb::check_cfg(cfg); if (e) return e;
     XRB_REQUIRE(n_rays >= 0 && max_samples > 0, "ngp_render: bad size");
     if (n_rays == 0) return XRB_OK;
-    XRB_REQUIRE(table_fp16 && weight_image && bitfield && rays_o && rays_d && bg3_host && rgb_out && alpha_out && numsteps && counters && workspace, "ngp_render: null pointer");
+    XRB_REQUIRE(table && weight_image && bitfield && rays_o && rays_d && bg3_host && rgb_out && alpha_out && numsteps && counters && workspace, "ngp_render: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     uint8_t *ws = (uint8_t *)workspace;
     size_t a = (xrb_rm_rays_sampler_workspace(n_rays) + 255) & ~(size_t)255;
@@ -37,9 +31,10 @@ int xrb_ngp_render(const xrb_ngp_config *cfg, const void *table_fp16, const void
                             numsteps, counters, ws, stream);
     if (e) return e;
     // counters[1] counts overflowed rays too; rows beyond max_samples do not exist, launch_field clamps to max_samples
-    if (g_ev_field0) cudaEventRecord(g_ev_field0, s);
-    e = xrb::launch_field(cfg, table_fp16, nullptr, nullptr, weight_image, coords, 7, coords + 4, 7, max_samples, counters + 1, raw, 1, false, s);
-    if (g_ev_field1) cudaEventRecord(g_ev_field1, s);
+    // measurement hook: events recorded right before / after the field kernel let a caller time the dominant kernel inside its own timed region
+    if (ev_before_field) cudaEventRecord((cudaEvent_t)ev_before_field, s);
+    e = xrb::launch_field(cfg, table, nullptr, nullptr, weight_image, coords, 7, coords + 4, 7, max_samples, counters + 1, raw, 1, false, s);
+    if (ev_after_field) cudaEventRecord((cudaEvent_t)ev_after_field, s);
     if (e) return e;
     return xrb_rm_calc_rgb_inference(raw, coords, numsteps, bg3_host, n_rays, rgb_act, dens_act, rgb_out, alpha_out, stream);
 }

@@ -479,7 +479,7 @@ using namespace xrb;
 // ============================================================================ C ABI
 extern "C" {
 
-int xrb_abi_version(void) { return 1; }
+int xrb_abi_version(void) { return 2; }   // 2: xrb_ngp_table (cell image), explicit profile events in xrb_ngp_render
 int xrb_built_for_sm(void) { return 100; }
 const char *xrb_last_error(void) { return g_err; }
 
@@ -609,17 +609,17 @@ int xrb_rm_ema_grid_samples(const float *grid_tmp, int n_elements, float decay, 
     return check_launch("ema");
 }
 
-int xrb_rm_update_bitfield(const float *grid, float *mean, uint8_t *bitfield, void *stream) {
-    XRB_REQUIRE(grid && mean && bitfield, "update_bitfield: null pointer");
-    XRB_REQUIRE(((uintptr_t)grid & 15) == 0 && ((uintptr_t)bitfield & 7) == 0, "update_bitfield: grid must be 16-byte, bitfield 8-byte aligned");
+size_t xrb_rm_update_bitfield_workspace(void) { return MEAN_BLOCKS * sizeof(float); }
+
+int xrb_rm_update_bitfield(const float *grid, float *mean, uint8_t *bitfield, void *workspace, void *stream) {
+    XRB_REQUIRE(grid && mean && bitfield && workspace, "update_bitfield: null pointer");
+    XRB_REQUIRE(((uintptr_t)grid & 15) == 0 && ((uintptr_t)bitfield & 7) == 0 && ((uintptr_t)workspace & 3) == 0, "update_bitfield: grid must be 16-byte, bitfield 8-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    // partial sums live in the (otherwise unused) tail of the reference's 16384-float density_grid_mean tensor when the caller passes
-    // one; to stay safe with a 1-float `mean` we keep a small static device scratch per device instead.
-    static float *partial[64] = {nullptr};
-    int dev = 0; cudaGetDevice(&dev);
-    if (!partial[dev]) { if (cudaMalloc(&partial[dev], MEAN_BLOCKS * sizeof(float)) != cudaSuccess) return check_launch("update_bitfield scratch"); }
-    grid_mean_partial_kernel<<<MEAN_BLOCKS, 1024, 0, s>>>((const float4 *)grid, partial[dev]);
-    grid_mean_final_kernel<<<1, 32, 0, s>>>(partial[dev], mean);
+    // the per-block partial sums of the fixed-order mean live in caller-owned scratch: no allocation inside the call (CUDA-graph capturable),
+    // nothing shared between streams or host threads
+    float *partial = (float *)workspace;
+    grid_mean_partial_kernel<<<MEAN_BLOCKS, 1024, 0, s>>>((const float4 *)grid, partial);
+    grid_mean_final_kernel<<<1, 32, 0, s>>>(partial, mean);
     uint32_t n_words = GRID_CELLS / 8 * NERF_CASCADES / 4;
     grid_to_bitfield_kernel<<<stream_grid(n_words), GRID_THREADS, 0, s>>>(n_words, (const float4 *)grid, (uint32_t *)bitfield, mean);
     for (uint32_t level = 1; level < NERF_CASCADES; ++level) {

@@ -91,13 +91,14 @@ __device__ __forceinline__ void tc_density_from_a(TcWarpgroup &c, const WeightIm
 #pragma unroll
     for (int k = 0; k < 16; ++k) dout[k] = round_h(dout[k]);
 }
-__device__ __forceinline__ void tc_density(TcWarpgroup &c, const WeightImageLayout &L, int density_hidden, const __half2 *__restrict__ table, const HashGridDev &g, float x, float y,
-                                           float z, float *dout) {
+template <int NP>
+__device__ __forceinline__ void tc_density(TcWarpgroup &c, const WeightImageLayout &L, int density_hidden, const __half2 *__restrict__ table, const uint8_t *__restrict__ cells,
+                                           const HashGridDev &g, float x, float y, float z, float *dout) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint32_t e[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { float2 f = hash_level(table, g, 4 * q + k, x, y, z); e[k] = pack_h2(f.x, f.y); }
+        for (int k = 0; k < 4; ++k) { float2 f = hash_level(table, cells, g, 4 * q + k, x, y, z, plan_mode<NP>(4 * q + k)); e[k] = pack_h2(f.x, f.y); }
         a_store_chunk(c, q, make_uint4(e[0], e[1], e[2], e[3]));
     }
     tc_density_from_a(c, L, density_hidden, dout);
@@ -126,10 +127,11 @@ __device__ __forceinline__ float4 tc_color_from_density(TcWarpgroup &c, const We
     return make_float4(round_h(cout[0]), round_h(cout[1]), round_h(cout[2]), dout[0]);
 }
 // Whole field: hash encode + both nets
+template <int NP>
 __device__ __forceinline__ float4 tc_field(TcWarpgroup &c, const WeightImageLayout &L, int density_hidden, int color_hidden, const __half2 *__restrict__ table,
-                                           const HashGridDev &g, float x, float y, float z, float dx, float dy, float dz) {
+                                           const uint8_t *__restrict__ cells, const HashGridDev &g, float x, float y, float z, float dx, float dy, float dz) {
     float dout[16];
-    tc_density(c, L, density_hidden, table, g, x, y, z, dout);
+    tc_density<NP>(c, L, density_hidden, table, cells, g, x, y, z, dout);
     return tc_color_from_density(c, L, color_hidden, dout, dx, dy, dz);
 }
 

@@ -34,6 +34,7 @@ class NerfRenderer:
         from .registry.networks import sample_pdf
         net = self.net
         n = rays_o.shape[0]
+        rays_o, rays_d, viewdirs = (x.contiguous().float() for x in (rays_o, rays_d, viewdirs))   # the kernels read dense [n,3] rows
         t = torch.linspace(0., 1., self.S, device=rays_o.device)
         z = (self.near * (1. - t) + self.far * t).expand(n, self.S).contiguous()           # GetZvals (create.py:502-531), lindisp=False
         data = {'rays_o': rays_o, 'rays_d': rays_d, 'viewdirs': viewdirs, 'z_vals': z}

@@ -2,6 +2,7 @@
 tensor-core weight image, and thin wrappers over the C ABI (include/xrnerf_b200.h: xrb_ngp_*).
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -19,8 +20,11 @@ class NgpField(nn.Module):
     """
 
     def __init__(self, n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=16, per_level_scale=PER_LEVEL_SCALE, width=64,
-                 density_hidden=1, color_hidden=2, seed=1337, impl=1):
+                 density_hidden=1, color_hidden=2, seed=1337, impl=1, n_packed_levels=None):
         super().__init__()
+        # levels [0, n_packed_levels) are gathered from the cell image (xrb_ngp_table, include/xrnerf_b200.h): 6 = the five dense levels + the
+        # first hashed one, 27.6 MB; 0 disables the image
+        self.n_packed = int(os.environ.get('XRB_PACKED_LEVELS', '6')) if n_packed_levels is None else int(n_packed_levels)
         self.cfg = _C.NgpConfig(n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, width, density_hidden, color_hidden)
         n_hash = _C.lib.xrb_tcnn_hashgrid_num_params(self.cfg)
         if n_hash < 0:
@@ -34,36 +38,61 @@ class NgpField(nn.Module):
         self.color_params = nn.Parameter(xavier([(width, 32)] + [(width, width)] * (color_hidden - 1) + [(16, width)]))
         self.impl = impl
         self._ver = None
-        self._table16 = self._dens16 = self._color16 = self._image = None
+        self._table16 = self._dens16 = self._color16 = self._image = self._cells = self.tab = None
 
-    # ---- fp16 working copies + packed UMMA weight image, refreshed when a master parameter changed
+    # ---- fp16 working copies, cell image and packed UMMA weight image, refreshed when a master parameter changed
+    def mark_dirty(self):
+        """Force the next refresh(). Parameter._version does not see writes through `.data` (mmcv's EMAHook swaps parameters with
+        `value.data.copy_(ema)`), so every entry point that may run after such a write calls this (val_step/test_step, load_state_dict, _apply)."""
+        self._ver = None
+
+    def _apply(self, fn, *a, **kw):
+        self.mark_dirty()
+        return super()._apply(fn, *a, **kw)
+
+    def _load_from_state_dict(self, *a, **kw):
+        self.mark_dirty()
+        return super()._load_from_state_dict(*a, **kw)
+
+    def _alloc(self, dev):
+        self._table16 = torch.empty(self.hash_params.numel(), dtype=torch.float16, device=dev)
+        self._dens16 = torch.empty(self.density_params.numel(), dtype=torch.float16, device=dev)
+        self._color16 = torch.empty(self.color_params.numel(), dtype=torch.float16, device=dev)
+        self._image = torch.empty(_C.lib.xrb_ngp_weight_image_bytes(self.cfg), dtype=torch.uint8, device=dev)
+        nb = _C.lib.xrb_ngp_cell_image_bytes(self.cfg, self.n_packed) if self.n_packed > 0 else 0
+        self._cells = torch.empty(nb, dtype=torch.uint8, device=dev) if nb else None
+        self.tab = _C.NgpTable(self._table16.data_ptr(), self._cells.data_ptr() if nb else None, self.n_packed if nb else 0)
+
+    def rebuild_cells(self):
+        """cell image <- fp16 table (one kernel; called whenever the table changed)"""
+        if self._cells is not None:
+            _C.check(_C.lib.xrb_ngp_build_cell_image(self.cfg, _C.ptr(self._table16), self.n_packed, _C.ptr(self._cells), _C.stream()), 'build cell image')
+
     def refresh(self, force=False):
         ver = (self.hash_params._version, self.density_params._version, self.color_params._version, self.hash_params.device)
         if not force and ver == self._ver:
             return
         dev = self.hash_params.device
         if self._table16 is None or self._table16.device != dev:
-            self._table16 = torch.empty(self.hash_params.numel(), dtype=torch.float16, device=dev)
-            self._dens16 = torch.empty(self.density_params.numel(), dtype=torch.float16, device=dev)
-            self._color16 = torch.empty(self.color_params.numel(), dtype=torch.float16, device=dev)
-            self._image = torch.empty(_C.lib.xrb_ngp_weight_image_bytes(self.cfg), dtype=torch.uint8, device=dev)
+            self._alloc(dev)
         s = _C.stream()
         _C.check(_C.lib.xrb_tcnn_cast_params(_C.ptr(self.hash_params.detach()), _C.ptr(self._table16), self.hash_params.numel(), s), 'cast hash')
         _C.check(_C.lib.xrb_tcnn_cast_params(_C.ptr(self.density_params.detach()), _C.ptr(self._dens16), self.density_params.numel(), s), 'cast density')
         _C.check(_C.lib.xrb_tcnn_cast_params(_C.ptr(self.color_params.detach()), _C.ptr(self._color16), self.color_params.numel(), s), 'cast color')
         _C.check(_C.lib.xrb_ngp_pack_weights(self.cfg, _C.ptr(self.density_params.detach()), _C.ptr(self.color_params.detach()), _C.ptr(self._image), s), 'pack')
+        self.rebuild_cells()
         self._ver = ver
 
     def run_mlp(self, pts, dirs, impl=None):
         """pts, dirs: [S,3] float32 views (row stride in floats may be > 3, e.g. coords[:, :3] / coords[:, 4:]). -> raw [S,4] f32."""
         _C.require_cuda(pts, dirs)
         self.refresh()
-        assert pts.dtype == torch.float32 and dirs.dtype == torch.float32 and pts.stride(1) == 1 and dirs.stride(1) == 1
+        (pp, ps), (dp, ds) = _C.rows(pts), _C.rows(dirs)
         n = pts.shape[0]
         raw = torch.empty((n, 4), dtype=torch.float32, device=pts.device)
         impl = self.impl if impl is None else impl
-        _C.check(_C.lib.xrb_ngp_mlp_forward(self.cfg, _C.ptr(self._table16), _C.ptr(self._dens16), _C.ptr(self._color16), _C.ptr(self._image), _C.ptr(pts),
-                                            pts.stride(0), _C.ptr(dirs), dirs.stride(0), n, _C.ptr(raw), impl, _C.stream()), 'ngp_mlp_forward')
+        _C.check(_C.lib.xrb_ngp_mlp_forward(self.cfg, self.tab, _C.ptr(self._dens16), _C.ptr(self._color16), _C.ptr(self._image), pp, ps, dp, ds, n, _C.ptr(raw), impl, _C.stream()),
+                 'ngp_mlp_forward')
         return raw
 
     def forward(self, pts, dirs):
@@ -79,19 +108,19 @@ class NgpField(nn.Module):
         if out is None:
             out = (torch.zeros_like(self.hash_params), torch.zeros_like(self.density_params), torch.zeros_like(self.color_params))
         n = pts.shape[0]
-        _C.check(_C.lib.xrb_ngp_mlp_backward(self.cfg, _C.ptr(self._table16), _C.ptr(self._dens16), _C.ptr(self._color16), _C.ptr(pts), pts.stride(0), _C.ptr(dirs),
-                                             dirs.stride(0), _C.ptr(grad_raw), n, _C.ptr(out[0]), _C.ptr(out[1]), _C.ptr(out[2]), _C.stream()), 'ngp_mlp_backward')
+        (pp, ps), (dp, ds) = _C.rows(pts), _C.rows(dirs)
+        _C.check(_C.lib.xrb_ngp_mlp_backward(self.cfg, self.tab, _C.ptr(self._dens16), _C.ptr(self._color16), pp, ps, dp, ds, _C.f32(grad_raw), n, _C.f32(out[0]), _C.f32(out[1]),
+                                             _C.f32(out[2]), _C.stream()), 'ngp_mlp_backward')
         return out
 
     def run_density(self, pts, impl=None):
         _C.require_cuda(pts)
         self.refresh()
-        assert pts.dtype == torch.float32 and pts.stride(1) == 1
+        pp, ps = _C.rows(pts)
         n = pts.shape[0]
         out = torch.empty((n, 1), dtype=torch.float32, device=pts.device)
         impl = self.impl if impl is None else impl
-        _C.check(_C.lib.xrb_ngp_density_forward(self.cfg, _C.ptr(self._table16), _C.ptr(self._dens16), _C.ptr(self._image), _C.ptr(pts), pts.stride(0), n,
-                                                _C.ptr(out), impl, _C.stream()), 'ngp_density_forward')
+        _C.check(_C.lib.xrb_ngp_density_forward(self.cfg, self.tab, _C.ptr(self._dens16), _C.ptr(self._image), pp, ps, n, _C.ptr(out), impl, _C.stream()), 'ngp_density_forward')
         return out
 
 
@@ -115,8 +144,24 @@ class _FieldFn(torch.autograd.Function):
         return None, None, None, dt, dd, dc
 
 
+def _rays(t):
+    """rays as the kernels read them: dense float32 [n,3] (a strided view - e.g. a Fortran-ordered array that came through torch.from_numpy - is
+    copied, never reinterpreted)"""
+    if t.dtype != torch.float32:
+        raise _C.XrbError(f'XRB_E_BADARG: rays must be float32, got {t.dtype}')
+    if t.dim() != 2 or t.shape[1] != 3:
+        raise _C.XrbError(f'XRB_E_BADARG: rays must be [n,3], got {tuple(t.shape)}')
+    return t.contiguous()
+
+
 class NgpRenderer:
-    """Fused inference render of a ray batch (xrb_ngp_render): march -> field -> composite, no host sync, persistent workspace."""
+    """Fused inference render of a ray batch (xrb_ngp_render / xrb_ngp_render_fused): march -> field -> composite, no host sync, persistent workspace.
+
+    samples_per_ray_budget sizes the sample buffers of the CHAIN path (n_rays * budget rows; the reference sizes them for 1024 per ray,
+    ngp_grid_sampler.py:47). A ray that does not fit gets count 0 exactly like the reference (ray_sampler.cu:76-82) and renders as background:
+    `overflowed(counters)` tells the caller (device-side compare, no sync), and HashNerfNetwork's validation uses the single-launch path, which
+    has no sample buffer and therefore no overflow. Returned tensors are cached per batch size and OVERWRITTEN by the next call with the same
+    size (pass `out=` to own them)."""
 
     def __init__(self, field, aabb=(0.0, 1.0), near=0.05, cone=1.0 / 256, rgb_act=2, dens_act=3, bg=(0.0, 0.0, 0.0), samples_per_ray_budget=64):
         self.field, self.aabb, self.near, self.cone = field, aabb, near, cone
@@ -125,13 +170,21 @@ class NgpRenderer:
         self.calls = 0
         self._ws = None
         self._out = {}
+        self._max_samples = 0
 
-    def render(self, rays_o, rays_d, bitfield, out=None):
+    def overflowed(self, counters):
+        """0-dim bool tensor (device): did the last chain render drop rays because the batch marched more samples than the budget holds?"""
+        return counters[1] > self._max_samples
+
+    def render(self, rays_o, rays_d, bitfield, out=None, profile_events=None):
+        """profile_events: optional (torch.cuda.Event, torch.cuda.Event) recorded right before / after the field kernel (bench roofline)."""
         _C.require_cuda(rays_o, rays_d, bitfield)
+        rays_o, rays_d = _rays(rays_o), _rays(rays_d)
         f = self.field
         f.refresh()
         n = rays_o.shape[0]
         max_samples = n * self.budget
+        self._max_samples = max_samples
         need = _C.lib.xrb_ngp_render_workspace(n, max_samples)
         if self._ws is None or self._ws.numel() < need or self._ws.device != rays_o.device:
             self._ws = torch.empty(need, dtype=torch.uint8, device=rays_o.device)
@@ -142,9 +195,12 @@ class NgpRenderer:
                                   torch.empty((n, 2), dtype=torch.int32, device=rays_o.device), torch.empty(2, dtype=torch.int32, device=rays_o.device))
             out = self._out[key]
         rgb, alpha, numsteps, counters = out
-        _C.check(_C.lib.xrb_ngp_render(f.cfg, _C.ptr(f._table16), _C.ptr(f._image), _C.ptr(bitfield), _C.ptr(rays_o), _C.ptr(rays_d), n, max_samples, self.aabb[0],
-                                       self.aabb[1], self.near, self.cone, 9121, self.calls, _C.float3(self.bg), self.rgb_act, self.dens_act, _C.ptr(rgb), _C.ptr(alpha),
-                                       _C.ptr(numsteps), _C.ptr(counters), _C.ptr(self._ws), _C.stream()), 'ngp_render')
+        ev0 = ev1 = None
+        if profile_events is not None:
+            ev0, ev1 = (_C.C.c_void_p(e.cuda_event) for e in profile_events)
+        _C.check(_C.lib.xrb_ngp_render(f.cfg, f.tab, _C.ptr(f._image), _C.u8(bitfield), _C.ptr(rays_o), _C.ptr(rays_d), n, max_samples, self.aabb[0],
+                                       self.aabb[1], self.near, self.cone, 9121, self.calls, _C.float3(self.bg), self.rgb_act, self.dens_act, _C.f32(rgb), _C.f32(alpha),
+                                       _C.i32(numsteps), _C.i32(counters), _C.ptr(self._ws), ev0, ev1, _C.stream()), 'ngp_render')
         self.calls += 1
         return rgb, alpha, numsteps, counters
 
@@ -152,6 +208,7 @@ class NgpRenderer:
         """Single-launch render (xrb_ngp_render_fused). Returns (rgb [n,3], alpha [n,1], n_samples i32[n]). `ws`: a zero-initialised workspace
         owned by the caller (one per stream when several batches are in flight); default: one per renderer."""
         _C.require_cuda(rays_o, rays_d, bitfield)
+        rays_o, rays_d = _rays(rays_o), _rays(rays_d)
         f = self.field
         f.refresh()
         n = rays_o.shape[0]
@@ -166,8 +223,8 @@ class NgpRenderer:
                                   torch.empty(n, dtype=torch.int32, device=rays_o.device))
             out = self._out[key]
         rgb, alpha, ns = out
-        _C.check(_C.lib.xrb_ngp_render_fused(f.cfg, _C.ptr(f._table16), _C.ptr(f._image), _C.ptr(bitfield), _C.ptr(rays_o), _C.ptr(rays_d), n, self.aabb[0], self.aabb[1],
-                                             self.near, self.cone, 9121, self.calls, _C.float3(self.bg), self.rgb_act, self.dens_act, _C.ptr(rgb), _C.ptr(alpha), _C.ptr(ns),
+        _C.check(_C.lib.xrb_ngp_render_fused(f.cfg, f.tab, _C.ptr(f._image), _C.u8(bitfield), _C.ptr(rays_o), _C.ptr(rays_d), n, self.aabb[0], self.aabb[1],
+                                             self.near, self.cone, 9121, self.calls, _C.float3(self.bg), self.rgb_act, self.dens_act, _C.f32(rgb), _C.f32(alpha), _C.i32(ns),
                                              _C.ptr(ws), _C.stream()), 'ngp_render_fused')
         self.calls += 1
         return rgb, alpha, ns

@@ -63,7 +63,12 @@ def ema_grid_samples_nerf_api(density_grid_tmp, n_elements, decay, density_grid)
 
 def update_bitfield_api(density_grid, density_grid_mean, density_grid_bitfield):
     _C.require_cuda(density_grid, density_grid_mean, density_grid_bitfield)
-    _C.check(_C.lib.xrb_rm_update_bitfield(_C.ptr(density_grid), _C.ptr(density_grid_mean), _C.ptr(density_grid_bitfield), _C.stream()), 'update_bitfield_api')
+    # scratch for the partial sums of the fixed-order mean: one small buffer per (device, stream), owned by this module
+    key = ('bitfield', density_grid.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _ws.get(key)
+    if ws is None:
+        ws = _ws[key] = torch.empty(_C.lib.xrb_rm_update_bitfield_workspace(), dtype=torch.uint8, device=density_grid.device)
+    _C.check(_C.lib.xrb_rm_update_bitfield(_C.f32(density_grid), _C.f32(density_grid_mean), _C.u8(density_grid_bitfield), _C.ptr(ws), _C.stream()), 'update_bitfield_api')
 
 
 def rays_sampler_api(rays_o, rays_d, density_grid_bitfield, metadata, imgs_id, xforms, aabb0, aabb1, near_distance, cone_angle_constant, coords_out,

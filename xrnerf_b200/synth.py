@@ -57,7 +57,9 @@ def get_rays_ngp(pose43, h=H, w=W, focal=FOCAL):
     rays_d = np.matmul(c2w[:3, :3], dirs[:, :, :, None])[..., 0]
     rays_d = rays_d / np.linalg.norm(rays_d, axis=-1, keepdims=True)
     rays_o = np.broadcast_to(c2w[:3, -1], rays_d.shape)
-    return rays_o.reshape(-1, 3).astype(np.float32), rays_d.reshape(-1, 3).astype(np.float32)
+    # C-contiguous on purpose: `broadcast_to(...).reshape(...).astype(...)` keeps the broadcast's zero strides ('K' order) and yields a
+    # Fortran-ordered [n,3] array, which torch.from_numpy(...).to(device) preserves
+    return np.ascontiguousarray(rays_o.reshape(-1, 3), dtype=np.float32), np.ascontiguousarray(rays_d.reshape(-1, 3), dtype=np.float32)
 
 
 def metadata_for(n_img, focal=FOCAL):

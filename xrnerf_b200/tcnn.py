@@ -77,10 +77,12 @@ class Encoding(nn.Module):
         n = x.shape[0]
         out = torch.empty((n, self.n_output_dims), dtype=torch.float16, device=x.device)
         if self.kind == 'hash':
-            _C.check(_C.lib.xrb_tcnn_hashgrid_forward(self.cfg, _C.ptr(self._shadow.get(self.params)), _C.ptr(x), x.stride(0), n, _C.ptr(out), _C.stream()),
-                     'hashgrid_forward')
+            tab = _C.NgpTable(self._shadow.get(self.params).data_ptr(), None, 0)
+            xp, xs = _C.rows(x)
+            _C.check(_C.lib.xrb_tcnn_hashgrid_forward(self.cfg, tab, xp, xs, n, _C.ptr(out), _C.stream()), 'hashgrid_forward')
         else:
-            _C.check(_C.lib.xrb_tcnn_sh4_forward(_C.ptr(x), x.stride(0), n, _C.ptr(out), _C.stream()), 'sh4_forward')
+            xp, xs = _C.rows(x)
+            _C.check(_C.lib.xrb_tcnn_sh4_forward(xp, xs, n, _C.ptr(out), _C.stream()), 'sh4_forward')
         return out
 
 

@@ -85,15 +85,15 @@ class NgpTrainer:
         self.coords_c.zero_()
         rm.compacted_coord_api(None, self.coords, self.numsteps, None, self.rgb_act, self.dens_act, self.aabb[0], self.aabb[1], self.coords_c, self.numsteps_c, self.cnt_c[0:1], self.cnt_c[1:2])
         n_rows = self.T
-        _C.check(_C.lib.xrb_ngp_mlp_forward(f.cfg, _C.ptr(f._table16), _C.ptr(f._dens16), _C.ptr(f._color16), _C.ptr(f._image), _C.ptr(self.coords_c), 7,
-                                            _C.ptr(self.coords_c[:, 4:]), 7, n_rows, _C.ptr(self.raw), 1, _C.stream()), 'field fwd')
+        pp, dp = _C.rows(self.coords_c[:, :3])[0], _C.rows(self.coords_c[:, 4:])[0]
+        _C.check(_C.lib.xrb_ngp_mlp_forward(f.cfg, f.tab, _C.ptr(f._dens16), _C.ptr(f._color16), _C.ptr(f._image), pp, 7, dp, 7, n_rows, _C.ptr(self.raw), 1, _C.stream()), 'field fwd')
         rm.calc_rgb_forward_api(self.raw, self.coords_c, self.numsteps, self.numsteps_c, bg, self.rgb_act, self.dens_act, 0.0, 1.0, self.rgb)
         loss, g = huber5_grad(self.rgb, target)
         self.draw.zero_()
         rm.calc_rgb_backward_api(self.raw, self.numsteps_c, self.coords_c, g, self.rgb, self.grid_mean, self.rgb_act, self.dens_act, 0.0, 1.0, self.draw)
         self.grads.zero_()
         gv = self.grads.views
-        _C.check(_C.lib.xrb_ngp_mlp_backward(f.cfg, _C.ptr(f._table16), _C.ptr(f._dens16), _C.ptr(f._color16), _C.ptr(self.coords_c), 7, _C.ptr(self.coords_c[:, 4:]), 7,
+        _C.check(_C.lib.xrb_ngp_mlp_backward(f.cfg, f.tab, _C.ptr(f._dens16), _C.ptr(f._color16), pp, 7, dp, 7,
                                              _C.ptr(self.draw), n_rows, _C.ptr(gv[0]), _C.ptr(gv[1]), _C.ptr(gv[2]), _C.stream()), 'field bwd')
         div = self.grads.allreduce(self.group)
         self.step_n += 1
@@ -104,5 +104,6 @@ class NgpTrainer:
             _C.check(_C.lib.xrb_adam_ema_step(_C.ptr(p.data), _C.ptr(p16), _C.ptr(g_), _C.ptr(m), _C.ptr(v), p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                                               self.step_n, div, _C.ptr(e), mom, _C.stream()), 'adam')
         _C.check(_C.lib.xrb_ngp_pack_weights(f.cfg, _C.ptr(f.density_params.data), _C.ptr(f.color_params.data), _C.ptr(f._image), _C.stream()), 'pack')
+        f.rebuild_cells()                                                               # the fp16 table changed: refresh its cell image
         f._ver = (f.hash_params._version, f.density_params._version, f.color_params._version, f.hash_params.device)  # shadows are current
         return loss
