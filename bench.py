@@ -5,8 +5,9 @@
 
 A "step" is one pass of the hot path (ray march -> hash/SH encode -> tiny MLPs -> alpha compositing) over one batch of
 65 536 synthetic Blender-shaped rays (800x800 spiral views, seeded lego-like occupancy grid, tcnn-default random weights).
-  value      device-timed rays/s with the ray batch already resident in HBM (CUDA events around each step, L2 flushed
-             between steps, max over ranks)
+  value      device-timed rays/s with the ray batches already resident in HBM (one CUDA-event pair around the K steps, max over
+             ranks); inputs larger than L2: 96 distinct ray batches (151 MB) are cycled, nothing is flushed (the 24.4 MB fp16 hash
+             table and its cell image are meant to stay L2-resident, as in production)
   e2e        the same metric through the public API with HOST (pinned) ray buffers: H2D of the rays and D2H of rgb+alpha
              inside the timed region
   roofline   dominant kernel (ngp_field_tc_kernel: hash gather + tcgen05 MLPs) timed live with CUDA events recorded inside the
@@ -219,10 +220,8 @@ def run_ours(args):
         with torch.cuda.stream(st):
             for e in evf[i]:
                 e.record(st)                          # materialise the cudaEvent_t handles
-            _C.lib.xrb_ngp_render_set_profile_events(_C.C.c_void_p(evf[i][0].cuda_event), _C.C.c_void_p(evf[i][1].cuda_event))
-            out = renderers[i % P].render(*dev_batches[(W + i) % N_BATCHES], bf)
+            out = renderers[i % P].render(*dev_batches[(W + i) % N_BATCHES], bf, profile_events=evf[i])
             counters_log.append(out[3].clone())
-    _C.lib.xrb_ngp_render_set_profile_events(None, None)
     join()
     e1.record(main)
     barrier()
@@ -339,6 +338,8 @@ def run_ours(args):
                 barrier()
                 i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 KI = 12
+                ns_acc = torch.zeros((), dtype=torch.float64, device=dev)
+                ns_acc += 0.0                                  # first-use kernels loaded before the timed region
                 i0.record()
                 for i in range(KI):
                     out_i = fn(*views[i % n_views])
@@ -347,8 +348,10 @@ def run_ours(args):
                 im = torch.tensor([i0.elapsed_time(i1)], dtype=torch.float64, device=dev)
                 if world > 1:
                     dist.all_reduce(im, op=dist.ReduceOp.MAX)
-                ns_i = out_i[2]
-                spr = float((ns_i[:, 0] if ns_i.dim() == 2 else ns_i).float().mean().item())
+                for v in range(n_views):                       # samples of EVERY timed image (the views are cycled; counts re-measured outside the timed region)
+                    ns_v = fn(*views[v])[2]
+                    ns_acc += (ns_v[:, 0] if ns_v.dim() == 2 else ns_v).double().sum() * (KI // n_views)
+                spr = float(ns_acc.item()) / (n_img * KI)
                 ms_img = float(im.item()) / KI
                 img_bytes = n_img * spr * (512 if path == 'fused' else BYTES_PER_SAMPLE) + n_img * 44          # gather (+ coords/raw round trip on the chain path) + ray I/O
                 pk, _ = peaks()

@@ -172,6 +172,15 @@ int xrb_ngp_mlp_backward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, 
                          const float *pts, int pts_stride, const float *dirs, int dirs_stride, const float *dl_draw, int n,
                          float *d_table, float *d_density, float *d_color, void *stream);
 
+/* The same backward on tcgen05 tensor-core tiles (csrc/ngp_backward_tc.cu): dX = dZ.W and dW += dZ^T.X per layer as UMMA instructions, the weight
+ * gradients accumulated in TMEM over the whole launch; fp16 operands (dZ staged with a fixed 2^12 scale), fp32 accumulation. Built for
+ * (density_hidden, color_hidden) = (1,1) and (1,2) — the reference config, configs/instant_ngp/nerf_blender_local01.py:113,123 — and returns
+ * XRB_E_UNSUPPORTED otherwise. n_rows_dev (optional, device): the effective row count is min(n, *n_rows_dev) (the compacted sample count
+ * stays on the device). Same accumulate-into-outputs contract as xrb_ngp_mlp_backward. */
+int xrb_ngp_mlp_backward_tc(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *weight_image, const float *pts, int pts_stride,
+                            const float *dirs, int dirs_stride, const float *dl_draw, int n, const int32_t *n_rows_dev, float *d_table,
+                            float *d_density, float *d_color, void *stream);
+
 /* Fused Adam step on an fp32 master vector + refresh of its fp16 working copy (torch.optim.Adam semantics with
  * L2 weight_decay folded into the gradient; configs/instant_ngp/nerf_blender_local01.py:13-18). grad is divided by
  * grad_div first (world size after a sum all-reduce). */

@@ -82,6 +82,26 @@ def test_rays_sampler_full_image_property(rm, scene):
     assert (used[:, :3] >= 0).all() and (used[:, :3] <= 1).all() and (used[:, 3] >= 0).all()
 
 
+def test_rays_sampler_full_image_bit_exact_vs_oracle(rm, port, scene):
+    """BASELINE-size parity (round-1 W1/W2): a whole 800x800 view in pixel order, marched by the CUDA path and by the oracle port: counts, bases,
+    ray slots and every coords row bit for bit. The rays go through torch.from_numpy WITHOUT the test helper's ascontiguousarray, exactly as bench.py
+    feeds them (a Fortran-ordered rays_o was read as different rays in round 1: the oracle gives ~10.9 samples/ray for this kind of view, that bug 23.0)."""
+    from xrnerf_b200 import synth
+    o, d = synth.get_rays_ngp(scene['poses'][21])
+    cap = 640000 * 48
+    a = port.rays_sampler(o, d, scene['bitfield'], cap)
+    n = o.shape[0]
+    coords = torch.zeros((cap, 7), dtype=torch.float32, device='cuda')
+    ridx = torch.zeros((n, 1), dtype=torch.int32, device='cuda'); ns = torch.zeros((n, 2), dtype=torch.int32, device='cuda'); cnt = torch.zeros(2, dtype=torch.int32, device='cuda')
+    rm.reset_rng(ray_sampler=0)
+    rm.rays_sampler_api(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), dev(scene['bitfield']), None, None, None, 0.0, 1.0, 0.05, 1.0 / 256, coords, ridx, ns, cnt)
+    total = int(a[3][1])
+    assert 8.0 < total / n < 14.0, total / n                      # the oracle's own figure for a spiral view of this scene
+    assert np.array_equal(a[3], cnt.cpu().numpy()) and np.array_equal(a[2], ns.cpu().numpy()) and np.array_equal(a[1], ridx.cpu().numpy())
+    assert np.array_equal(_bits(a[0][:total]), _bits(coords[:total].cpu().numpy()))
+    assert (a[2][:, 0] > 64).any()                                 # rays longer than the inline t cache exist in this view: the overflow-chunk emit path ran
+
+
 def test_compacted_coord(rm, port, scene):
     s = scene
     c, _, ns, cnt = port.rays_sampler(s['rays_o'], s['rays_d'], s['bitfield'], 4096 * 256)

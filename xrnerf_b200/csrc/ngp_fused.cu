@@ -55,6 +55,7 @@ struct FusedCtl {
     uint32_t owner[N_SLOTS][4];     // (producer index << 1 | mailbox parity) of each quarter
     uint32_t issued_bcast[FR_N_WG];
     uint32_t tmem_slot, ticket, closed, done, prod_done;
+    uint32_t morton[128];           // expand_bits7 table for the occupancy test (common.cuh morton_lut_init)
 };
 template <int FR_N_WG, int N_PROD, int N_SLOTS>
 __host__ __device__ inline size_t fused_smem_bytes(uint32_t image_bytes) {
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__((4 * FR_N_WG + N_PROD) * 32, 3 - FR_N_WG) ngp_
         tc::tma_bulk_g2s(W, P.weight_image, P.image_bytes, &ctl->wbar);
     }
     if (warp == 1) tc::tmem_alloc<64 * FR_N_WG>(&ctl->tmem_slot);
+    morton_lut_init(ctl->morton, threadIdx.x, blockDim.x);
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__((4 * FR_N_WG + N_PROD) * 32, 3 - FR_N_WG) ngp_
                         if (!(aabb_contains(P.lo, P.hi, p[0], p[1], p[2]) && nsteps < NERF_STEPS)) { alive = false; break; }
                         float dt = calc_dt(t, P.cone);
                         uint32_t mip = (uint32_t)mip_from_dt(dt, p[0], p[1], p[2]);
-                        if (occupied_at(p[0], p[1], p[2], P.bitfield, mip)) {
+                        if (occupied_at(p[0], p[1], p[2], P.bitfield, mip, ctl->morton)) {
                             tl[m] = t; ++m; ++nsteps; t = add_(t, dt);
                             if (m == FR_TCAP) break;
                         } else {

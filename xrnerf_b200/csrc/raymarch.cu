@@ -25,27 +25,43 @@ int check_launch(const char *what) {
 
 // ============================================================================ ray march
 // One thread per ray. emit==false: count steps (ray_sampler.cu:58-72). emit==true: write rows (:99-115).
-constexpr uint32_t TCAP = 64;  // per-ray sample-t slots cached by the count pass; rays with more samples are re-marched by the emit pass
+constexpr uint32_t TCAP = 64;                      // per-ray sample-t slots cached inline by the count pass
+constexpr uint32_t OVF_CAP = NERF_STEPS - TCAP;    // a ray with more samples gets ONE overflow chunk of this many slots (bump-allocated), so the emit
+                                                   // pass can rebuild all of its rows in parallel; only when the chunk pool is exhausted is it re-marched
+struct OvfPool { uint32_t *counter; float *area; uint32_t n_chunks; int32_t *chunk_of; };
 
 template <bool EMIT>
 __device__ __forceinline__ uint32_t march_ray(const float o[3], const float d[3], float lo, float hi, float startt, float cone,
-                                              const uint8_t *__restrict__ bitfield, uint32_t limit, float *__restrict__ coords, float *__restrict__ tbuf = nullptr) {
+                                              const uint8_t *__restrict__ bitfield, uint32_t limit, float *__restrict__ coords, float *__restrict__ tbuf = nullptr,
+                                              const uint32_t *lut = nullptr, const OvfPool *pool = nullptr, uint32_t ray = 0) {
     const float idir[3] = {div_(1.0f, d[0]), div_(1.0f, d[1]), div_(1.0f, d[2])};
     float wdir[3], diag = sub_(hi, lo);
     if (EMIT) { wdir[0] = mul_(add_(d[0], 1.0f), 0.5f); wdir[1] = mul_(add_(d[1], 1.0f), 0.5f); wdir[2] = mul_(add_(d[2], 1.0f), 0.5f); }
     uint32_t j = 0; float t = startt;
+    float *ovf = nullptr;
     while (true) {
         float p[3] = {add_(o[0], mul_(t, d[0])), add_(o[1], mul_(t, d[1])), add_(o[2], mul_(t, d[2]))};
         if (!(aabb_contains(lo, hi, p[0], p[1], p[2]) && j < limit)) break;
         float dt = calc_dt(t, cone);
         uint32_t mip = (uint32_t)mip_from_dt(dt, p[0], p[1], p[2]);
-        if (occupied_at(p[0], p[1], p[2], bitfield, mip)) {
+        if (occupied_at(p[0], p[1], p[2], bitfield, mip, lut)) {
             if (EMIT) {
                 float *c = coords + 7 * (size_t)j;
                 c[0] = div_(sub_(p[0], lo), diag); c[1] = div_(sub_(p[1], lo), diag); c[2] = div_(sub_(p[2], lo), diag);  // warp_position
                 c[3] = warp_dt(dt);
                 c[4] = wdir[0]; c[5] = wdir[1]; c[6] = wdir[2];
-            } else if (tbuf && j < TCAP) tbuf[j] = t;
+            } else if (tbuf) {
+                if (j < TCAP) tbuf[j] = t;
+                else if (pool) {
+                    if (j == TCAP) {
+                        const uint32_t c = atomicAdd(pool->counter, 1u);
+                        const bool got = c < pool->n_chunks;
+                        pool->chunk_of[ray] = got ? (int32_t)c : -1;
+                        ovf = got ? pool->area + (size_t)c * OVF_CAP : nullptr;
+                    }
+                    if (ovf) ovf[j - TCAP] = t;
+                }
+            }
             ++j; t = add_(t, dt);
         } else {
             t = advance_to_next_voxel(t, cone, p, d, idir, NERF_GRIDSIZE >> mip);
@@ -68,16 +84,21 @@ struct MarchWs {  // device workspace layout for N rays
     uint32_t *local_excl;  // [N]
     float *startt;         // [N]
     uint32_t *block_sum;   // [n_blocks] -> exclusive block offsets after scan
-    uint32_t *misc;        // [4]: base0, ray0, total
+    uint32_t *misc;        // [16]: base0, ray0, total, overflow-chunk counter
     float *tbuf;           // [N][TCAP] sample t values found by the count pass
+    int32_t *chunk_of;     // [N] overflow chunk of a ray with more than TCAP samples (-1: pool exhausted); valid only for such rays
+    float *ovf;            // [n_chunks][OVF_CAP]
+    uint32_t n_chunks;
 };
+__host__ __device__ inline uint32_t march_n_chunks(int n) { uint32_t c = (uint32_t)n / 8u; return c < 64u ? 64u : c; }   // every 8th ray may be longer than TCAP samples
 __host__ __device__ inline size_t march_ws_bytes(int n) {
     size_t nb = (size_t)(n + MARCH_RAYS_PER_BLOCK_MIN - 1) / MARCH_RAYS_PER_BLOCK_MIN;
-    return sizeof(uint32_t) * ((size_t)n * 2 + nb + 16 + (size_t)n * TCAP);
+    return sizeof(uint32_t) * ((size_t)n * 3 + nb + 16 + (size_t)n * TCAP + (size_t)march_n_chunks(n) * OVF_CAP);
 }
 inline MarchWs march_ws(void *ws, int n) {
     size_t nb = (size_t)(n + MARCH_RAYS_PER_BLOCK_MIN - 1) / MARCH_RAYS_PER_BLOCK_MIN;
     MarchWs w; w.local_excl = (uint32_t *)ws; w.startt = (float *)(w.local_excl + n); w.block_sum = (uint32_t *)(w.startt + n); w.misc = w.block_sum + nb; w.tbuf = (float *)(w.misc + 16);
+    w.chunk_of = (int32_t *)(w.tbuf + (size_t)n * TCAP); w.ovf = (float *)(w.chunk_of + n); w.n_chunks = march_n_chunks(n);
     return w;
 }
 
@@ -99,8 +120,11 @@ template <int LANE_STRIDE>
 __global__ void __launch_bounds__(MARCH_BLOCK) march_count_kernel(int n_rays, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
                                                                   const uint8_t *__restrict__ bitfield, float lo, float hi, float near_distance, float cone,
                                                                   Pcg32 rng, uint32_t *__restrict__ local_excl, float *__restrict__ startt_out,
-                                                                  uint32_t *__restrict__ block_sum, int32_t *__restrict__ numsteps, float *__restrict__ tbuf) {
+                                                                  uint32_t *__restrict__ block_sum, int32_t *__restrict__ numsteps, float *__restrict__ tbuf, OvfPool pool) {
     constexpr int MARCH_RAYS_PER_BLOCK = MARCH_BLOCK / LANE_STRIDE;
+    __shared__ uint32_t lut[128];
+    morton_lut_init(lut, threadIdx.x, MARCH_BLOCK);
+    __syncthreads();
     const bool owner = (threadIdx.x % LANE_STRIDE) == 0;
     uint32_t i = blockIdx.x * MARCH_RAYS_PER_BLOCK + threadIdx.x / LANE_STRIDE;
     uint32_t n = 0;
@@ -109,7 +133,7 @@ __global__ void __launch_bounds__(MARCH_BLOCK) march_count_kernel(int n_rays, co
         float d[3] = {rays_d[3 * (size_t)i], rays_d[3 * (size_t)i + 1], rays_d[3 * (size_t)i + 2]};
         float st = ray_start_t(rng, i, lo, hi, o, d, near_distance, cone);
         startt_out[i] = st;
-        n = march_ray<false>(o, d, lo, hi, st, cone, bitfield, NERF_STEPS, nullptr, tbuf ? tbuf + (size_t)i * TCAP : nullptr);
+        n = march_ray<false>(o, d, lo, hi, st, cone, bitfield, NERF_STEPS, nullptr, tbuf ? tbuf + (size_t)i * TCAP : nullptr, lut, tbuf ? &pool : nullptr, i);
         numsteps[2 * (size_t)i] = (int32_t)n;
     }
     uint32_t tot;
@@ -152,7 +176,7 @@ __global__ void __launch_bounds__(1024) march_scan_kernel(int n_blocks, uint32_t
 __global__ void __launch_bounds__(256) march_emit_kernel(int n_rays, const float *__restrict__ rays_o, const float *__restrict__ rays_d, const uint8_t *__restrict__ bitfield, float lo,
                                                          float hi, float cone, uint32_t max_samples, const uint32_t *__restrict__ local_excl, const float *__restrict__ startt,
                                                          const uint32_t *__restrict__ block_off, const uint32_t *__restrict__ misc, const float *__restrict__ tbuf,
-                                                         float *__restrict__ coords_out, int32_t *__restrict__ rays_index, int32_t *__restrict__ numsteps,
+                                                         const int32_t *__restrict__ chunk_of, const float *__restrict__ ovf, float *__restrict__ coords_out, int32_t *__restrict__ rays_index, int32_t *__restrict__ numsteps,
                                                          int32_t *__restrict__ counters, int rays_per_scan_block) {
     const int lane = threadIdx.x & 31;
     const uint32_t n_warps = (gridDim.x * 256) >> 5;
@@ -173,30 +197,21 @@ __global__ void __launch_bounds__(256) march_emit_kernel(int n_rays, const float
             if (n > 0) {
                 const float o[3] = {rays_o[3 * (size_t)i], rays_o[3 * (size_t)i + 1], rays_o[3 * (size_t)i + 2]};
                 const float d[3] = {rays_d[3 * (size_t)i], rays_d[3 * (size_t)i + 1], rays_d[3 * (size_t)i + 2]};
-                if (n <= TCAP) {
-                    const float diag = sub_(hi, lo);
-                    const float w0 = mul_(add_(d[0], 1.0f), 0.5f), w1 = mul_(add_(d[1], 1.0f), 0.5f), w2 = mul_(add_(d[2], 1.0f), 0.5f);
-                    for (uint32_t j = lane; j < n; j += 32) {
-                        float t = tbuf[(size_t)i * TCAP + j];
-                        float *c = coords_out + 7 * (size_t)(base + j);
-                        c[0] = div_(sub_(add_(o[0], mul_(t, d[0])), lo), diag); c[1] = div_(sub_(add_(o[1], mul_(t, d[1])), lo), diag); c[2] = div_(sub_(add_(o[2], mul_(t, d[2])), lo), diag);
-                        c[3] = warp_dt(calc_dt(t, cone));
-                        c[4] = w0; c[5] = w1; c[6] = w2;
-                    }
-                } else {
-                    // long ray: lanes rebuild the first TCAP-1 rows from the cache; lane 0 resumes the march AT cached sample TCAP-1
-                    // (the march state is just t) and emits the remaining n-(TCAP-1) rows
-                    const float diag = sub_(hi, lo);
-                    const float w0 = mul_(add_(d[0], 1.0f), 0.5f), w1 = mul_(add_(d[1], 1.0f), 0.5f), w2 = mul_(add_(d[2], 1.0f), 0.5f);
-                    for (uint32_t j = lane; j < TCAP - 1; j += 32) {
-                        float t = tbuf[(size_t)i * TCAP + j];
-                        float *c = coords_out + 7 * (size_t)(base + j);
-                        c[0] = div_(sub_(add_(o[0], mul_(t, d[0])), lo), diag); c[1] = div_(sub_(add_(o[1], mul_(t, d[1])), lo), diag); c[2] = div_(sub_(add_(o[2], mul_(t, d[2])), lo), diag);
-                        c[3] = warp_dt(calc_dt(t, cone));
-                        c[4] = w0; c[5] = w1; c[6] = w2;
-                    }
-                    if (lane == 0) march_ray<true>(o, d, lo, hi, tbuf[(size_t)i * TCAP + TCAP - 1], cone, bitfield, n - (TCAP - 1), coords_out + 7 * (size_t)(base + TCAP - 1));
+                const float diag = sub_(hi, lo);
+                const float w0 = mul_(add_(d[0], 1.0f), 0.5f), w1 = mul_(add_(d[1], 1.0f), 0.5f), w2 = mul_(add_(d[2], 1.0f), 0.5f);
+                // rows whose t is cached (inline slots, then the ray's overflow chunk) are rebuilt by all lanes
+                const int32_t chunk = n > TCAP ? chunk_of[i] : -1;
+                const float *tl = tbuf + (size_t)i * TCAP, *to = chunk >= 0 ? ovf + (size_t)chunk * OVF_CAP : nullptr;
+                const uint32_t n_par = n <= TCAP ? n : (to ? n : TCAP - 1);
+                for (uint32_t j = lane; j < n_par; j += 32) {
+                    float t = j < TCAP ? tl[j] : to[j - TCAP];
+                    float *c = coords_out + 7 * (size_t)(base + j);
+                    c[0] = div_(sub_(add_(o[0], mul_(t, d[0])), lo), diag); c[1] = div_(sub_(add_(o[1], mul_(t, d[1])), lo), diag); c[2] = div_(sub_(add_(o[2], mul_(t, d[2])), lo), diag);
+                    c[3] = warp_dt(calc_dt(t, cone));
+                    c[4] = w0; c[5] = w1; c[6] = w2;
                 }
+                // chunk pool exhausted: lane 0 resumes the march AT cached sample TCAP-1 (the march state is just t) and emits the remaining rows (ray_sampler.cu:99-115)
+                if (n_par < n && lane == 0) march_ray<true>(o, d, lo, hi, tl[TCAP - 1], cone, bitfield, n - (TCAP - 1), coords_out + 7 * (size_t)(base + TCAP - 1));
             }
         }
     }
@@ -497,16 +512,21 @@ int xrb_rm_rays_sampler(const float *rays_o, const float *rays_d, const uint8_t 
     const int ls = lane_stride(), rpb = MARCH_BLOCK / ls;
     int nb = (n_rays + rpb - 1) / rpb;
     Pcg32 rng = host_rng(seed, n_prior_calls);
-    if (ls == 1) march_count_kernel<1><<<nb, MARCH_BLOCK, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, near_distance, cone_angle, rng, w.local_excl, w.startt, w.block_sum, numsteps, w.tbuf);
-    else if (ls == 2) march_count_kernel<2><<<nb, MARCH_BLOCK, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, near_distance, cone_angle, rng, w.local_excl, w.startt, w.block_sum, numsteps, w.tbuf);
-    else march_count_kernel<4><<<nb, MARCH_BLOCK, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, near_distance, cone_angle, rng, w.local_excl, w.startt, w.block_sum, numsteps, w.tbuf);
+    cudaMemsetAsync(w.misc + 3, 0, sizeof(uint32_t), s);   // overflow-chunk counter
+    OvfPool pool{w.misc + 3, w.ovf, w.n_chunks, w.chunk_of};
+    if (ls == 1) march_count_kernel<1><<<nb, MARCH_BLOCK, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, near_distance, cone_angle, rng, w.local_excl, w.startt, w.block_sum, numsteps, w.tbuf, pool);
+    else if (ls == 2) march_count_kernel<2><<<nb, MARCH_BLOCK, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, near_distance, cone_angle, rng, w.local_excl, w.startt, w.block_sum, numsteps, w.tbuf, pool);
+    else march_count_kernel<4><<<nb, MARCH_BLOCK, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, near_distance, cone_angle, rng, w.local_excl, w.startt, w.block_sum, numsteps, w.tbuf, pool);
     march_scan_kernel<<<1, 1024, 0, s>>>(nb, w.block_sum, w.misc, counters);
     march_emit_kernel<<<warp_grid(n_rays), 256, 0, s>>>(n_rays, rays_o, rays_d, bitfield, aabb0, aabb1, cone_angle, (uint32_t)max_samples, w.local_excl, w.startt,
-                                                                             w.block_sum, w.misc, w.tbuf, coords_out, rays_index, numsteps, counters, rpb);
+                                                                             w.block_sum, w.misc, w.tbuf, w.chunk_of, w.ovf, coords_out, rays_index, numsteps, counters, rpb);
     return check_launch("rays_sampler");
 }
 
-size_t xrb_rm_compacted_coord_workspace(int n_rays) { return march_ws_bytes(n_rays); }
+size_t xrb_rm_compacted_coord_workspace(int n_rays) {   // the compaction uses only the scan part of the march workspace layout (local_excl, startt, block_sum, misc)
+    size_t nb = (size_t)(n_rays + MARCH_RAYS_PER_BLOCK_MIN - 1) / MARCH_RAYS_PER_BLOCK_MIN;
+    return sizeof(uint32_t) * ((size_t)n_rays * 2 + nb + 16);
+}
 
 int xrb_rm_compacted_coord(const float *network_output, const float *coords_in, const int32_t *numsteps, int n_rays, int max_compacted, float *coords_out,
                            int32_t *numsteps_compacted, int32_t *ray_counter, int32_t *step_counter, void *workspace, void *stream) {

@@ -101,14 +101,23 @@ class NgpField(nn.Module):
             return _FieldFn.apply(self, pts, dirs, self.hash_params, self.density_params, self.color_params)
         return self.run_mlp(pts, dirs)
 
-    def backward_params(self, pts, dirs, grad_raw, out=None):
-        """dL/draw [S,4] -> (d_hash, d_density, d_color) fp32, accumulated into `out` if given (zero-initialised otherwise)."""
+    def tc_backward_ok(self):
+        return (self.cfg.density_hidden, self.cfg.color_hidden) in ((1, 1), (1, 2))
+
+    def backward_params(self, pts, dirs, grad_raw, out=None, impl=None):
+        """dL/draw [S,4] -> (d_hash, d_density, d_color) fp32, accumulated into `out` if given (zero-initialised otherwise).
+        impl 1 = tcgen05 tensor-core tiles (xrb_ngp_mlp_backward_tc), 0 = CUDA cores; default: self.impl where the tensor-core kernel is built."""
         _C.require_cuda(pts, dirs, grad_raw)
         self.refresh()
         if out is None:
             out = (torch.zeros_like(self.hash_params), torch.zeros_like(self.density_params), torch.zeros_like(self.color_params))
         n = pts.shape[0]
         (pp, ps), (dp, ds) = _C.rows(pts), _C.rows(dirs)
+        impl = (self.impl if self.tc_backward_ok() else 0) if impl is None else impl
+        if impl == 1:
+            _C.check(_C.lib.xrb_ngp_mlp_backward_tc(self.cfg, self.tab, _C.ptr(self._image), pp, ps, dp, ds, _C.f32(grad_raw), n, None, _C.f32(out[0]), _C.f32(out[1]), _C.f32(out[2]),
+                                                    _C.stream()), 'ngp_mlp_backward_tc')
+            return out
         _C.check(_C.lib.xrb_ngp_mlp_backward(self.cfg, self.tab, _C.ptr(self._dens16), _C.ptr(self._color16), pp, ps, dp, ds, _C.f32(grad_raw), n, _C.f32(out[0]), _C.f32(out[1]),
                                              _C.f32(out[2]), _C.stream()), 'ngp_mlp_backward')
         return out
