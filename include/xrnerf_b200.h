@@ -158,10 +158,12 @@ int xrb_tcnn_mlp_forward(const void *params_fp16, const void *x_fp16, int n, int
 
 /* HashNerfMLP.run_mlp (hashnerf_mlp.py:55-79) fused: pts/dirs f32 rows (stride in floats, so `coords[:, :3]` /
  * `coords[:, 4:]` views of a [S,7] buffer work in place) -> raw f32[n,4] = (rgb3, density1).
- * impl: 0 = SIMT (CUDA cores), 1 = tcgen05 tensor-core tiles (weights from `weight_image`). */
+ * impl: 0 = SIMT (CUDA cores), 1 = tcgen05 tensor-core tiles (weights from `weight_image`).
+ * n_rows_dev (optional, device pointer): the effective row count is min(n, *n_rows_dev) — a sample count produced on the device by the
+ * march / compaction never has to visit the host. */
 int xrb_ngp_mlp_forward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *density_fp16, const void *color_fp16,
                         const void *weight_image, const float *pts, int pts_stride, const float *dirs, int dirs_stride, int n,
-                        float *raw, int impl, void *stream);
+                        const int32_t *n_rows_dev, float *raw, int impl, void *stream);
 /* HashNerfMLP.run_density (hashnerf_mlp.py:107-111): -> density f32[n] (raw, pre-activation) */
 int xrb_ngp_density_forward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *density_fp16, const void *weight_image,
                             const float *pts, int pts_stride, int n, float *density, int impl, void *stream);
@@ -191,6 +193,17 @@ int xrb_adam_step(float *param, void *param_fp16, const float *grad, float *exp_
  * ema f32[n] (NULL = no EMA), initialised by the caller as a copy of param (EMAHook.before_run). */
 int xrb_adam_ema_step(float *param, void *param_fp16, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int step, float grad_div, float *ema, float ema_momentum, void *stream);
+
+/* The same step reading a bf16 gradient (the wire format of the sharded data-parallel step in xrnerf_b200/train.py: reduce-scatter of bf16
+ * gradients -> this Adam on the rank's own shard of (param, exp_avg, exp_avg_sq, ema) -> all-gather of the refreshed fp16 working copy). */
+int xrb_adam_ema_step_bf16grad(float *param, void *param_fp16, const void *grad_bf16, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int step, float grad_div, float *ema, float ema_momentum,
+                               void *stream);
+/* fp32 -> bf16 (round to nearest even), n elements */
+int xrb_pack_bf16(const float *src, void *dst_bf16, int64_t n, void *stream);
+/* HashNerfNetwork.train_step's loss (xrnerf/models/networks/hashnerf.py:39-44, utils/metrics.py:8-16): 5 * HuberLoss(delta, reduction 'sum') over
+ * n_elements values; writes d loss / d rgb and ADDS the loss value to *loss_accum (device float), one pass. */
+int xrb_ngp_huber5_grad(const float *rgb, const float *target, int64_t n_elements, float delta, float *grad_out, float *loss_accum, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused render of a ray batch (inference): replaces the chain

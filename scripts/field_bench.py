@@ -47,12 +47,14 @@ print('march (memset + count + scan + emit) us: median %.1f min %.1f' % timed(ma
 march(0); torch.cuda.synchronize()
 S = int(cnt[1].item())
 print('samples', S, 'per ray', S / N)
-plans = [int(a) for a in sys.argv[1:]] or [0, 5, 6, 7]
+plans = [int(a) for a in sys.argv[1:]] or [0, 6, 7]
 for npk in plans:
     f = NgpField(n_packed_levels=npk).to(dev)
     with torch.no_grad():
         f.hash_params.copy_(torch.from_numpy(table).to(dev)); f.density_params.copy_(torch.from_numpy(dens).to(dev)); f.color_params.copy_(torch.from_numpy(color).to(dev))
     f.refresh()
+    torch.cuda.synchronize()
+    print('n_packed=%d: cell image %.2f GB' % (npk, (f._cells.numel() if f._cells is not None else 0) / 1e9), flush=True)
     c = coords[:S]
     med, mn = timed(lambda i: f.run_mlp(c[:, :3], c[:, 4:]))
     print('field n_packed=%d regs=%s: median %.1f us min %.1f us -> %.0f GB/s algorithmic (556 B/sample)' % (npk, os.environ.get('XRB_TC_REGS', '96'), med, mn, S * 556 / med / 1e3))

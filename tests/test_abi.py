@@ -99,18 +99,18 @@ def test_cell_image_layout_and_validation_without_gpu():
     cfg = _C.NgpConfig(16, 2, 19, 16, 1.38191288, 64, 1, 2)
     res = (C.c_uint32 * 16)()
     assert lib.xrb_tcnn_hashgrid_layout(cfg, None, None, res) == 0
-    for n in range(0, 9):
+    for n in range(0, 9):                                                                                       # (up to 13 levels may be packed; 9+ are GB-sized)
         assert lib.xrb_ngp_cell_image_bytes(cfg, n) == 32 * sum(int(r) ** 3 for r in list(res)[:n])           # one 32-byte record per grid cell
     assert lib.xrb_ngp_cell_image_bytes(cfg, 6) == 32 * (16 ** 3 + 23 ** 3 + 31 ** 3 + 43 ** 3 + 59 ** 3 + 81 ** 3)
     assert lib.xrb_ngp_build_cell_image(cfg, None, 0, None, None) == 0
-    assert lib.xrb_ngp_build_cell_image(cfg, None, 9, None, None) == -1
+    assert lib.xrb_ngp_build_cell_image(cfg, None, 14, None, None) == -1
     assert lib.xrb_ngp_build_cell_image(cfg, None, 5, None, None) == -1 and b'null' in lib.xrb_last_error()
     buf = (C.c_char * 256)()
     a = (C.addressof(buf) + 63) & ~63
     tab = _C.NgpTable(a, a + 4, 6)                                                                              # cell image not 32-byte aligned
     out = C.c_void_p(a)
-    assert lib.xrb_ngp_mlp_forward(cfg, tab, None, None, out, out, 3, out, 3, 4, out, 1, None) == -1 and b'cell image' in lib.xrb_last_error()
-    assert lib.xrb_ngp_mlp_forward(cfg, None, None, None, out, out, 3, out, 3, 4, out, 1, None) == -1
+    assert lib.xrb_ngp_mlp_forward(cfg, tab, None, None, out, out, 3, out, 3, 4, None, out, 1, None) == -1 and b'cell image' in lib.xrb_last_error()
+    assert lib.xrb_ngp_mlp_forward(cfg, None, None, None, out, out, 3, out, 3, 4, None, out, 1, None) == -1
     assert lib.xrb_rm_update_bitfield(out, out, out, None, None) == -1                                          # scratch is the caller's
     assert lib.xrb_rm_update_bitfield_workspace() == 512 * 4
 

@@ -62,12 +62,15 @@ _SIGS = {
     'xrb_tcnn_hashgrid_forward': (_i, [_cfg, _tab, P, _i, _i, P, P]),
     'xrb_tcnn_sh4_forward': (_i, [P, _i, _i, P, P]),
     'xrb_tcnn_mlp_forward': (_i, [P, P, _i, _i, _i, _i, P, P]),
-    'xrb_ngp_mlp_forward': (_i, [_cfg, _tab, P, P, P, P, _i, P, _i, _i, P, _i, P]),
+    'xrb_ngp_mlp_forward': (_i, [_cfg, _tab, P, P, P, P, _i, P, _i, _i, P, P, _i, P]),
     'xrb_ngp_density_forward': (_i, [_cfg, _tab, P, P, P, _i, _i, P, _i, P]),
     'xrb_ngp_mlp_backward': (_i, [_cfg, _tab, P, P, P, _i, P, _i, P, _i, P, P, P, P]),
     'xrb_ngp_mlp_backward_tc': (_i, [_cfg, _tab, P, P, _i, P, _i, P, _i, P, P, P, P, P]),
     'xrb_adam_step': (_i, [P, P, P, P, P, _i64, _f, _f, _f, _f, _f, _i, _f, P]),
     'xrb_adam_ema_step': (_i, [P, P, P, P, P, _i64, _f, _f, _f, _f, _f, _i, _f, P, _f, P]),
+    'xrb_adam_ema_step_bf16grad': (_i, [P, P, P, P, P, _i64, _f, _f, _f, _f, _f, _i, _f, P, _f, P]),
+    'xrb_pack_bf16': (_i, [P, P, _i64, P]),
+    'xrb_ngp_huber5_grad': (_i, [P, P, _i64, _f, P, P, P]),
     'xrb_ngp_render_workspace': (_sz, [_i, _i]),
     'xrb_ngp_render_fused_workspace': (_sz, []),
     'xrb_ngp_render_fused': (_i, [_cfg, _tab, P, P, P, P, _i, _f, _f, _f, _f, _u64, _i64, C.POINTER(C.c_float), _i, _i, P, P, P, P, P]),

@@ -13,6 +13,7 @@
 // oracle_ngp_mlp_backward); the dY staging uses fp16 with a fixed 2^12 scale (tcnn uses fp16 + loss scale 128).
 // v1 runs the GEMM-shaped parts on CUDA cores; moving dX/dW onto tcgen05 tiles is the next step.
 #include "ngp_field.cuh"
+#include <cuda_bf16.h>
 
 namespace xrb {
 
@@ -266,11 +267,16 @@ static int launch_bwd(const HashGridDev &g, const void *table, const void *cells
 }
 
 // ---------------------------------------------------------------------------- fused Adam (+ fp16 shadow refresh)
-__global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, __half *__restrict__ p16, const float *__restrict__ grad, float *__restrict__ m, float *__restrict__ v, int64_t n,
+template <typename G> __device__ __forceinline__ float grad_load(const G *g, int64_t i);
+template <> __device__ __forceinline__ float grad_load<float>(const float *g, int64_t i) { return g[i]; }
+template <> __device__ __forceinline__ float grad_load<__nv_bfloat16>(const __nv_bfloat16 *g, int64_t i) { return __bfloat162float(g[i]); }
+
+template <typename G>
+__global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, __half *__restrict__ p16, const G *__restrict__ grad, float *__restrict__ m, float *__restrict__ v, int64_t n,
                                                    float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt_inv, float grad_mul, float *__restrict__ ema, float ema_m) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float w = p[i];
-        float gval = grad[i] * grad_mul + wd * w;                    // torch.optim.Adam: weight_decay folded into the gradient
+        float gval = grad_load<G>(grad, i) * grad_mul + wd * w;       // torch.optim.Adam: weight_decay folded into the gradient
         float mi = b1 * m[i] + (1.f - b1) * gval;
         float vi = b2 * v[i] + (1.f - b2) * gval * gval;
         m[i] = mi; v[i] = vi;
@@ -282,11 +288,59 @@ __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, __half
     }
 }
 
+// fp32 gradient -> bf16 (the wire format of the sharded data-parallel step: reduce-scatter in bf16, see xrnerf_b200/train.py)
+__global__ void __launch_bounds__(256) pack_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int64_t n) {
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (; i + 3 < n; i += stride) {
+        float4 v = *reinterpret_cast<const float4 *>(src + i);
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o; o.x = *reinterpret_cast<uint32_t *>(&a); o.y = *reinterpret_cast<uint32_t *>(&b);
+        *reinterpret_cast<uint2 *>(dst + i) = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 4) { int64_t t = (n & ~(int64_t)3) + threadIdx.x; if (t < n) dst[t] = __float2bfloat16_rn(src[t]); }
+}
+
+// 5 * HuberLoss(delta, 'sum') of HashNerfNetwork.train_step (networks/utils/metrics.py:8-16, hashnerf.py:39-44): gradient wrt rgb and the loss value in ONE pass
+__global__ void __launch_bounds__(256) huber5_kernel(const float *__restrict__ rgb, const float *__restrict__ target, int64_t n, float delta, float *__restrict__ grad, float *__restrict__ loss_accum) {
+    float local = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float diff = rgb[i] - target[i], rel = fabsf(diff);
+        local += rel > delta ? rel - 0.5f * delta : (0.5f / delta) * rel * rel;
+        grad[i] = 5.f * (rel > delta ? copysignf(1.f, diff) : diff / delta);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    __shared__ float part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) { float t = 0.f; for (int k = 0; k < 8; ++k) t += part[k]; atomicAdd(loss_accum, 5.f * t); }
+}
+
 }  // namespace xrb
 
 using namespace xrb;
 
 extern "C" {
+
+int xrb_ngp_huber5_grad(const float *rgb, const float *target, int64_t n_elements, float delta, float *grad_out, float *loss_accum, void *stream) {
+    XRB_REQUIRE(n_elements >= 0 && delta > 0.f, "huber5_grad: bad arguments");
+    if (n_elements == 0) return XRB_OK;
+    XRB_REQUIRE(rgb && target && grad_out && loss_accum, "huber5_grad: null pointer");
+    int64_t blocks = (n_elements + 255) / 256; if (blocks > NUM_SMS * 8) blocks = NUM_SMS * 8;
+    huber5_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(rgb, target, n_elements, delta, grad_out, loss_accum);
+    return check_launch("huber5_grad");
+}
+
+int xrb_pack_bf16(const float *src, void *dst_bf16, int64_t n, void *stream) {
+    XRB_REQUIRE(n >= 0, "pack_bf16: negative size");
+    if (n == 0) return XRB_OK;
+    XRB_REQUIRE(src && dst_bf16, "pack_bf16: null pointer");
+    XRB_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst_bf16 & 7) == 0, "pack_bf16: misaligned");
+    int64_t blocks = (n / 4 + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16; if (blocks < 1) blocks = 1;
+    pack_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16 *)dst_bf16, n);
+    return check_launch("pack_bf16");
+}
 
 int xrb_ngp_mlp_backward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *density_fp16, const void *color_fp16, const float *pts, int pts_stride, const float *dirs,
                          int dirs_stride, const float *dl_draw, int n, float *d_table, float *d_density, float *d_color, void *stream) {
@@ -309,16 +363,30 @@ int xrb_adam_step(float *param, void *param_fp16, const float *grad, float *exp_
     return xrb_adam_ema_step(param, param_fp16, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_div, nullptr, 0.f, stream);
 }
 
-int xrb_adam_ema_step(float *param, void *param_fp16, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                      int step, float grad_div, float *ema, float ema_momentum, void *stream) {
+static int adam_launch(float *param, void *param_fp16, const void *grad, bool grad_bf16, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int step, float grad_div, float *ema, float ema_momentum, void *stream) {
     XRB_REQUIRE(n >= 0 && step >= 1 && grad_div != 0.f && ema_momentum >= 0.f && ema_momentum <= 1.f, "adam_step: bad arguments");
     if (n == 0) return XRB_OK;
     XRB_REQUIRE(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
     double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
     int64_t blocks = (n + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
-    adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, (__half *)param_fp16, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
-                                                              (float)(1.0 / sqrt(bc2)), 1.f / grad_div, ema, ema_momentum);
+    if (grad_bf16)
+        adam_kernel<__nv_bfloat16><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, (__half *)param_fp16, (const __nv_bfloat16 *)grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                                                                 (float)bc1, (float)(1.0 / sqrt(bc2)), 1.f / grad_div, ema, ema_momentum);
+    else
+        adam_kernel<float><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, (__half *)param_fp16, (const float *)grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, (float)bc1,
+                                                                         (float)(1.0 / sqrt(bc2)), 1.f / grad_div, ema, ema_momentum);
     return check_launch("adam_step");
+}
+
+int xrb_adam_ema_step(float *param, void *param_fp16, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int step, float grad_div, float *ema, float ema_momentum, void *stream) {
+    return adam_launch(param, param_fp16, grad, false, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_div, ema, ema_momentum, stream);
+}
+
+int xrb_adam_ema_step_bf16grad(float *param, void *param_fp16, const void *grad_bf16, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1, float beta2, float eps,
+                               float weight_decay, int step, float grad_div, float *ema, float ema_momentum, void *stream) {
+    return adam_launch(param, param_fp16, grad_bf16, true, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_div, ema, ema_momentum, stream);
 }
 
 }  // extern "C"

@@ -52,7 +52,9 @@ inline size_t cell_image_layout(HashGridDev *g, int n_packed) {
     }
     return rec * 32;
 }
-constexpr int MAX_PACKED_LEVELS = 8;   // level 7 (res 154) is 117 MB of records; beyond that the image outgrows any cache
+constexpr int MAX_PACKED_LEVELS = 13;  // image sizes for the reference grid: ..6 = 73 MB, ..7 = 190 MB (about what the 126 MB L2 still helps with), ..9 = 1.3 GB, ..12 = 25 GB;
+                                       // levels past the L2 are served by HBM at ONE 32-byte sector per sample and level, where the hashed table costs ~4.5 sectors of L2
+                                       // traffic (4 (y,z) rows, the x neighbour shares the sector in 7 of 8 cases). Level 13 alone would be 39 GB.
 __host__ __device__ inline int64_t mlp_num_params(int in_w, int width, int n_hidden, int out_pad) { return (int64_t)width * in_w + (int64_t)(n_hidden - 1) * width * width + (int64_t)out_pad * width; }
 
 inline int check_cfg(const xrb_ngp_config *cfg) {

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) cell_image_build_kernel(HashGridDev g, co
         const uint32_t rec = (uint32_t)(t >> 3), c = (uint32_t)t & 7u;
         int l = 0;
 #pragma unroll
-        for (int k = 1; k < MAX_PACKED_LEVELS; ++k) if (k < n_packed && rec >= g.cell_off[k]) l = k;
+        for (int k = 1; k < MAX_PACKED_LEVELS; ++k) if (k < n_packed && rec >= g.cell_off[k]) l = k;   // cell_off is increasing
         const uint32_t res = g.res[l], cell = rec - g.cell_off[l];
         const uint32_t gx = cell % res, gy = (cell / res) % res, gz = cell / (res * res);
         const uint32_t hs = g.offset[l + 1] - g.offset[l];
@@ -250,7 +250,7 @@ size_t xrb_ngp_cell_image_bytes(const xrb_ngp_config *cfg, int n_packed_levels) 
 
 int xrb_ngp_build_cell_image(const xrb_ngp_config *cfg, const void *table_fp16, int n_packed_levels, void *cell_image, void *stream) {
     int e = check_cfg(cfg); if (e) return e;
-    XRB_REQUIRE(n_packed_levels >= 0 && n_packed_levels <= MAX_PACKED_LEVELS, "build_cell_image: n_packed_levels must be 0..8");
+    XRB_REQUIRE(n_packed_levels >= 0 && n_packed_levels <= MAX_PACKED_LEVELS, "build_cell_image: n_packed_levels must be 0..13");
     if (n_packed_levels == 0) return XRB_OK;
     XRB_REQUIRE(table_fp16 && cell_image, "build_cell_image: null pointer");
     XRB_REQUIRE(((uintptr_t)cell_image & 31) == 0 && ((uintptr_t)table_fp16 & 15) == 0, "build_cell_image: cell image must be 32-byte, table 16-byte aligned");
@@ -268,7 +268,7 @@ int table_setup(const xrb_ngp_config *cfg, const xrb_ngp_table *t, HashGridDev *
     if (!t || !t->table_fp16) { set_error("null hash table"); return XRB_E_BADARG; }
     if (((uintptr_t)t->table_fp16 & 15) != 0) { set_error("hash table must be 16-byte aligned"); return XRB_E_BADARG; }
     hashgrid_build(cfg, g);
-    if (t->n_packed_levels < 0 || t->n_packed_levels > MAX_PACKED_LEVELS) { set_error("n_packed_levels must be 0..8"); return XRB_E_BADARG; }
+    if (t->n_packed_levels < 0 || t->n_packed_levels > MAX_PACKED_LEVELS) { set_error("n_packed_levels must be 0..13"); return XRB_E_BADARG; }
     if (t->n_packed_levels > 0) {
         if (!t->cell_image || ((uintptr_t)t->cell_image & 31) != 0) { set_error("cell image missing or not 32-byte aligned"); return XRB_E_BADARG; }
         cell_image_layout(g, t->n_packed_levels);
@@ -335,8 +335,9 @@ int launch_field(const xrb_ngp_config *cfg, const xrb_ngp_table *tab, const void
         // for the (latency-bound, 36-register) march kernel of the NEXT batch to co-reside on another stream.
         static const int variant = getenv("XRB_TC_REGS") ? atoi(getenv("XRB_TC_REGS")) : 96;
         const int regs = variant == 128 ? 128 : 96;
-        // static gather plan: the kernel is specialised for "levels [0,NP) packed, all others hashed" (NP = 5, 6, 7); anything else takes the run-time form
-        const int np = (plan_valid(g, tab->n_packed_levels) && tab->n_packed_levels >= 5 && tab->n_packed_levels <= 7) ? tab->n_packed_levels : 0;
+        // static gather plan: the kernel is specialised for "levels [0,NP) packed, all others hashed" (NP = 6, 7, 12); anything else takes the run-time form
+        const int npl = tab->n_packed_levels;
+        const int np = (plan_valid(g, npl) && (npl == 6 || npl == 7 || npl == 12)) ? npl : 0;
         int n_tiles = (n + 127) / 128;
 #define XRB_LAUNCH_TC(D, R, NP)                                                                                                                     \
     do {                                                                                                                                            \
@@ -347,7 +348,7 @@ int launch_field(const xrb_ngp_config *cfg, const xrb_ngp_table *tab, const void
     } while (0)
 #define XRB_LAUNCH_TC_NP(D, R)                                                                                                                      \
     do {                                                                                                                                            \
-        if (np == 5) XRB_LAUNCH_TC(D, R, 5); else if (np == 6) XRB_LAUNCH_TC(D, R, 6); else if (np == 7) XRB_LAUNCH_TC(D, R, 7); else XRB_LAUNCH_TC(D, R, 0); \
+        if (np == 6) XRB_LAUNCH_TC(D, R, 6); else if (np == 7) XRB_LAUNCH_TC(D, R, 7); else if (np == 12) XRB_LAUNCH_TC(D, R, 12); else XRB_LAUNCH_TC(D, R, 0); \
     } while (0)
         if (density_only) { if (regs == 128) XRB_LAUNCH_TC_NP(true, 128); else XRB_LAUNCH_TC_NP(true, 96); }
         else { if (regs == 128) XRB_LAUNCH_TC_NP(false, 128); else XRB_LAUNCH_TC_NP(false, 96); }
@@ -360,14 +361,14 @@ int launch_field(const xrb_ngp_config *cfg, const xrb_ngp_table *tab, const void
 extern "C" {
 
 int xrb_ngp_mlp_forward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *density_fp16, const void *color_fp16, const void *weight_image, const float *pts, int pts_stride,
-                        const float *dirs, int dirs_stride, int n, float *raw, int impl, void *stream) {
+                        const float *dirs, int dirs_stride, int n, const int32_t *n_rows_dev, float *raw, int impl, void *stream) {
     int e = check_cfg(cfg); if (e) return e;
     XRB_REQUIRE(n >= 0 && pts_stride >= 3 && dirs_stride >= 3, "ngp_mlp_forward: bad size");
     if (n == 0) return XRB_OK;
     XRB_REQUIRE(table && pts && dirs && raw, "ngp_mlp_forward: null pointer");
     XRB_REQUIRE(((uintptr_t)raw & 15) == 0, "ngp_mlp_forward: raw must be 16-byte aligned");
     XRB_REQUIRE(impl == 0 ? (density_fp16 && color_fp16) : (weight_image != nullptr), "ngp_mlp_forward: missing weights for the requested impl");
-    return launch_field(cfg, table, density_fp16, color_fp16, weight_image, pts, pts_stride, dirs, dirs_stride, n, nullptr, raw, impl, false, (cudaStream_t)stream);
+    return launch_field(cfg, table, density_fp16, color_fp16, weight_image, pts, pts_stride, dirs, dirs_stride, n, n_rows_dev, raw, impl, false, (cudaStream_t)stream);
 }
 
 int xrb_ngp_density_forward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *density_fp16, const void *weight_image, const float *pts, int pts_stride, int n, float *density,

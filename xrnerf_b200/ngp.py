@@ -91,7 +91,7 @@ class NgpField(nn.Module):
         n = pts.shape[0]
         raw = torch.empty((n, 4), dtype=torch.float32, device=pts.device)
         impl = self.impl if impl is None else impl
-        _C.check(_C.lib.xrb_ngp_mlp_forward(self.cfg, self.tab, _C.ptr(self._dens16), _C.ptr(self._color16), _C.ptr(self._image), pp, ps, dp, ds, n, _C.ptr(raw), impl, _C.stream()),
+        _C.check(_C.lib.xrb_ngp_mlp_forward(self.cfg, self.tab, _C.ptr(self._dens16), _C.ptr(self._color16), _C.ptr(self._image), pp, ps, dp, ds, n, None, _C.ptr(raw), impl, _C.stream()),
                  'ngp_mlp_forward')
         return raw
 

@@ -1,18 +1,30 @@
 """Fused Instant-NGP training step (HashNerfNetwork.train_step, /root/reference/xrnerf/models/networks/hashnerf.py:32-52 +
 ngp_grid_sampler.py:189-266 + the mmcv OptimizerHook/Adam it runs under) without host synchronisation:
 
-  march -> compaction -> field forward (tcgen05) -> composite forward -> Huber x5 loss -> composite backward ->
-  field backward (one kernel) -> [all-reduce of ONE flat fp32 gradient buffer] -> fused Adam (+ fp16 / UMMA-image refresh)
+  [aux stream, one step ahead]  march -> compaction            (needs only rays + occupancy bitfield, not the weights)
+  [main stream]  field forward (tcgen05) -> composite forward -> Huber x5 loss+grad (one kernel) -> composite backward ->
+                 field backward (tcgen05: dX and dW as UMMA instructions) -> gradient exchange -> fused Adam (+ fp16 / UMMA-image / cell-image refresh)
 
-Data parallel: every rank holds identical weights and takes a disjoint ray batch; the only collective is the gradient
-all-reduce (what MMDistributedDataParallel does implicitly in the reference, core/apis/train.py:28-36); the sum is divided by
-world size inside the Adam kernel. The occupancy grid is updated identically on every rank (same weights + same RNG call
-index => same grid), so it needs no communication.
+Every per-sample kernel reads the compacted sample count on the device (`n_rows_dev`), so the work follows the batch actually marched.
+
+Rays trained per step. The reference compacts a batch to `target_batch_size` = 2^18 samples by truncation in ray order (compacted_coord.cu:5-77) and keeps the
+batch near that size with `update_batch_rays` (ngp_grid_sampler.py:268-281: every 16 steps n_rays <- ceil128(n_rays * 2^18 / mean compacted count)). A fixed
+65 536-ray batch of the benchmark scene marches ~700 K samples, so with T = 2^18 most rays would be truncated away and never trained; `NgpTrainer` therefore
+takes T as a parameter (bench: 2^20, nothing truncated), reports `trained_rays()` (rays whose every sample took part), and implements the reference's
+adaptive rule for callers that size the batch like the reference does (`adaptive_n_rays`).
+
+Data parallel (world > 1): every rank holds identical weights and takes a disjoint ray batch. The gradient exchange of the 12.2 M-entry hash table is SHARDED
+(what MMDistributedDataParallel's dense fp32 all-reduce does in the reference, core/apis/train.py:28-36, at a quarter of the bytes):
+  bf16 pack -> reduce-scatter (each rank receives the sum of ITS 1/world slice) -> Adam on the rank's slice of (master, exp_avg, exp_avg_sq, ema) ->
+  all-gather of the refreshed fp16 working copy
+so a rank moves 2 x 24.4 MB x (world-1)/world instead of 2 x 48.8 MB x (world-1)/world, and runs 1/world of the Adam pass. The fp32 master / EMA slices of
+the other ranks are fetched on demand (`sync_master()`: checkpointing, validation with EMA weights). The ~10 K MLP weights use a plain fp32 all-reduce.
+`grad_comm='allreduce'` keeps the dense fp32 all-reduce of round 1. The march of step k+1 runs on the aux stream while step k's exchange is in flight.
+The occupancy grid is updated identically on every rank (same weights + same RNG call index => same grid), so it needs no communication.
 """
 import torch
 
 from . import _C
-from . import raymarch_cuda as rm
 
 
 class FlatGradBuffer:
@@ -38,8 +50,60 @@ class FlatGradBuffer:
         return 1.0
 
 
+def shard_range(n, world, rank, align=8):
+    """[begin, end) of rank's slice of an n-element vector cut into `world` equal slices of ceil(n / world) rounded up to `align` elements
+    (the last slices may be short or empty); `padded` = world * slice length is the size collectives operate on."""
+    per = -(-n // world)
+    per = -(-per // align) * align
+    b = min(rank * per, n)
+    return b, min(b + per, n), per, per * world
+
+
+class ShardedExchange:
+    """Host logic of the sharded gradient exchange for ONE parameter vector (device-agnostic: the gloo CPU test runs it).
+
+    reduce_scatter_sum(src)  -> this rank's slice of sum_over_ranks(src)   (src: padded wire-format vector)
+    all_gather(full, mine)   -> every rank's slice written into `full` (padded)
+    Backends without reduce_scatter (gloo) fall back to all_reduce + slice: same result, used only by the CPU test."""
+
+    def __init__(self, n, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n = n
+        self.begin, self.end, self.per, self.padded = shard_range(n, self.world, self.rank)
+
+    def reduce_scatter_sum(self, src, out):
+        assert src.numel() == self.padded and out.numel() == self.per
+        if self.world == 1:
+            out.copy_(src[:self.per])
+            return out
+        try:
+            self.dist.reduce_scatter_tensor(out, src, op=self.dist.ReduceOp.SUM, group=self.group)
+        except (RuntimeError, NotImplementedError):
+            tmp = src.clone()
+            self.dist.all_reduce(tmp, op=self.dist.ReduceOp.SUM, group=self.group)
+            out.copy_(tmp[self.rank * self.per:(self.rank + 1) * self.per])
+        return out
+
+    def all_gather(self, full, mine):
+        assert full.numel() == self.padded and mine.numel() == self.per
+        if self.world == 1:
+            full[:self.per].copy_(mine)
+            return full
+        try:
+            self.dist.all_gather_into_tensor(full, mine, group=self.group)
+        except (RuntimeError, NotImplementedError):
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            self.dist.all_gather(parts, mine, group=self.group)
+            full.copy_(torch.cat(parts))
+        return full
+
+
 def huber5_grad(rgb, target, delta=0.1):
-    """d/d rgb of 5 * HuberLoss(rgb, target, 0.1, 'sum') (networks/utils/metrics.py:8-16, hashnerf.py:39-44) and the loss value."""
+    """d/d rgb of 5 * HuberLoss(rgb, target, 0.1, 'sum') (networks/utils/metrics.py:8-16, hashnerf.py:39-44) and the loss value (torch restatement of
+    xrb_ngp_huber5_grad, kept for the CPU tests that pin it to the reference's own metrics.py)."""
     diff = rgb - target
     rel = diff.abs()
     loss = torch.where(rel > delta, rel - 0.5 * delta, 0.5 / delta * rel * rel).sum() * 5
@@ -47,63 +111,222 @@ def huber5_grad(rgb, target, delta=0.1):
     return loss, grad
 
 
-class NgpTrainer:
-    def __init__(self, field, bitfield, n_rays, target_batch_size=1 << 18, aabb=(0.0, 1.0), near=0.05, cone=1.0 / 256, rgb_act=2, dens_act=3,
-                 lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay=1e-6, samples_per_ray_budget=64, group=None, ema_momentum=None, ema_warm_up=100):
-        self.f, self.bitfield, self.n_rays, self.T = field, bitfield, n_rays, target_batch_size
-        self.aabb, self.near, self.cone, self.rgb_act, self.dens_act = aabb, near, cone, rgb_act, dens_act
-        self.lr, self.betas, self.eps, self.wd, self.group = lr, betas, eps, weight_decay, group
-        dev = field.hash_params.device
-        self.params = [field.hash_params, field.density_params, field.color_params]
-        self.grads = FlatGradBuffer(self.params)
-        self.m = [torch.zeros_like(p) for p in self.params]
-        self.v = [torch.zeros_like(p) for p in self.params]
-        self.step_n = 0
-        # EMAHook(momentum=0.05) of the reference config (nerf_blender_local01.py:24), folded into the Adam pass; buffers start as copies (EMAHook.before_run)
-        self.ema_momentum, self.ema_warm_up = ema_momentum, ema_warm_up
-        self.ema = [p.detach().clone() for p in self.params] if ema_momentum is not None else [None] * len(self.params)
-        cap = n_rays * samples_per_ray_budget
+def adaptive_n_rays(n_rays, measured_total, n_steps=16, target_batch_size=1 << 18):
+    """update_batch_rays (ngp_grid_sampler.py:268-281): n_rays <- min(ceil128(n_rays * T / max(measured / n_steps, 1)), 2^18)"""
+    measured = max(measured_total / float(n_steps), 1.0)
+    n = int(n_rays * target_batch_size / measured)
+    n = (n + 127) // 128 * 128
+    return min(n, 1 << 18)
+
+
+class _Slot:
+    """sample buffers of one in-flight batch (two slots: the march of step k+1 runs while step k trains)"""
+
+    def __init__(self, n_rays, cap, T, dev):
         self.coords = torch.empty((cap, 7), dtype=torch.float32, device=dev)
-        self.coords_c = torch.zeros((self.T, 7), dtype=torch.float32, device=dev)
-        self.raw = torch.empty((self.T, 4), dtype=torch.float32, device=dev)
-        self.draw = torch.zeros((self.T, 4), dtype=torch.float32, device=dev)
+        self.coords_c = torch.zeros((T, 7), dtype=torch.float32, device=dev)
         self.rays_index = torch.zeros((n_rays, 1), dtype=torch.int32, device=dev)
         self.numsteps = torch.zeros((n_rays, 2), dtype=torch.int32, device=dev)
         self.numsteps_c = torch.zeros((n_rays, 2), dtype=torch.int32, device=dev)
         self.counter = torch.zeros(2, dtype=torch.int32, device=dev)
         self.cnt_c = torch.zeros(2, dtype=torch.int32, device=dev)
-        self.rgb = torch.zeros((n_rays, 3), dtype=torch.float32, device=dev)
-        self.grid_mean = torch.ones(1, dtype=torch.float32, device=dev)
-        field.refresh()
+        self.ws_march = torch.empty(_C.lib.xrb_rm_rays_sampler_workspace(n_rays), dtype=torch.uint8, device=dev)
+        self.ws_compact = torch.empty(_C.lib.xrb_rm_compacted_coord_workspace(n_rays), dtype=torch.uint8, device=dev)
+        self.ready = None          # event: march + compaction of the batch in this slot are done
+        self.free = None           # event: the training step that used this slot has finished reading it
+        self.rays = None
 
-    def step(self, rays_o, rays_d, target, bg):
+
+class NgpTrainer:
+    def __init__(self, field, bitfield, n_rays, target_batch_size=1 << 18, aabb=(0.0, 1.0), near=0.05, cone=1.0 / 256, rgb_act=2, dens_act=3,
+                 lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay=1e-6, samples_per_ray_budget=64, group=None, ema_momentum=None, ema_warm_up=100,
+                 grad_comm='sharded', bwd_impl=None):
+        import torch.distributed as dist
+        self.f, self.bitfield, self.n_rays, self.T = field, bitfield, n_rays, int(target_batch_size)
+        self.aabb, self.near, self.cone, self.rgb_act, self.dens_act = aabb, near, cone, rgb_act, dens_act
+        self.lr, self.betas, self.eps, self.wd, self.group = lr, betas, eps, weight_decay, group
+        dev = field.hash_params.device
+        self.dev = dev
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.grad_comm = grad_comm if self.world > 1 else 'none'
+        self.bwd_impl = (1 if field.tc_backward_ok() else 0) if bwd_impl is None else bwd_impl
+        self.params = [field.hash_params, field.density_params, field.color_params]
+        field.refresh()
+        n_hash = field.hash_params.numel()
+        self.ex = ShardedExchange(n_hash, group) if self.grad_comm == 'sharded' else None
+        pad = self.ex.padded if self.ex else n_hash
+        # flat fp32 gradient: [hash (padded to the collective's size) | density | colour]
+        self.gflat = torch.zeros(pad + field.density_params.numel() + field.color_params.numel(), dtype=torch.float32, device=dev)
+        self.g_hash = self.gflat[:n_hash]
+        self.g_mlp = self.gflat[pad:]
+        self.g_dens = self.g_mlp[:field.density_params.numel()]
+        self.g_color = self.g_mlp[field.density_params.numel():]
+        self.grads = [self.g_hash, self.g_dens, self.g_color]
+        if self.ex:
+            self.g16 = torch.zeros(pad, dtype=torch.bfloat16, device=dev)                 # wire format of the hash gradient
+            self.g16_mine = torch.zeros(self.ex.per, dtype=torch.bfloat16, device=dev)
+            b, e = self.ex.begin, self.ex.end
+            self.m = [torch.zeros(e - b, device=dev), torch.zeros_like(field.density_params), torch.zeros_like(field.color_params)]
+            self.v = [torch.zeros(e - b, device=dev), torch.zeros_like(field.density_params), torch.zeros_like(field.color_params)]
+            self.t16_pad = torch.zeros(pad, dtype=torch.float16, device=dev)               # all-gather target (padded copy of the fp16 table)
+        else:
+            self.m = [torch.zeros_like(p) for p in self.params]
+            self.v = [torch.zeros_like(p) for p in self.params]
+        self.step_n = 0
+        # EMAHook(momentum=0.05) of the reference config (nerf_blender_local01.py:24), folded into the Adam pass; buffers start as copies (EMAHook.before_run)
+        self.ema_momentum, self.ema_warm_up = ema_momentum, ema_warm_up
+        if ema_momentum is not None:
+            self.ema = [p.detach().clone() for p in self.params]
+            if self.ex:
+                self.ema[0] = field.hash_params.detach()[self.ex.begin:self.ex.end].clone()
+        else:
+            self.ema = [None] * 3
+        cap = n_rays * samples_per_ray_budget
+        self.slots = [_Slot(n_rays, cap, self.T, dev) for _ in range(2)]
+        self.raw = torch.empty((self.T, 4), dtype=torch.float32, device=dev)
+        self.draw = torch.zeros((self.T, 4), dtype=torch.float32, device=dev)
+        self.rgb = torch.zeros((n_rays, 3), dtype=torch.float32, device=dev)
+        self.grad_rgb = torch.zeros((n_rays, 3), dtype=torch.float32, device=dev)
+        self.loss_accum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.grid_mean = torch.ones(1, dtype=torch.float32, device=dev)
+        self.aux = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None
+        self.march_calls = 0
+        self.cur = 0
+        self.master_stale = False
+
+    # ------------------------------------------------------------------ march + compaction of one batch (aux stream)
+    def _prepare(self, slot, rays_o, rays_d):
+        from .ngp import _rays
+        rays_o, rays_d = _rays(rays_o), _rays(rays_d)
+        s = self.slots[slot]
+        main = torch.cuda.current_stream()
+        entry = torch.cuda.Event(); entry.record(main)
+        with torch.cuda.stream(self.aux):
+            self.aux.wait_event(entry)                 # the rays exist
+            if s.free is not None:
+                self.aux.wait_event(s.free)            # the step that last used this slot is done with it
+            s.counter.zero_(); s.cnt_c.zero_()
+            n = rays_o.shape[0]
+            st = _C.stream()
+            _C.check(_C.lib.xrb_rm_rays_sampler(_C.ptr(rays_o), _C.ptr(rays_d), _C.u8(self.bitfield), None, None, None, n, s.coords.shape[0], self.aabb[0], self.aabb[1], self.near,
+                                                self.cone, 9121, self.march_calls, _C.ptr(s.coords), _C.ptr(s.rays_index), _C.ptr(s.numsteps), _C.ptr(s.counter), _C.ptr(s.ws_march), st),
+                     'rays_sampler')
+            self.march_calls += 1
+            # the reference's no-grad pre-pass over ALL samples (ngp_grid_sampler.py:229-230) feeds only compacted_coord's dead transmittance loop
+            # (compacted_coord.cu:41-44, SURVEY Q3): skipping it changes no result. Padding rows of coords_c are never read: every consumer takes the
+            # compacted count from the device (cnt_c[1]).
+            _C.check(_C.lib.xrb_rm_compacted_coord(None, _C.ptr(s.coords), _C.ptr(s.numsteps), n, self.T, _C.ptr(s.coords_c), _C.ptr(s.numsteps_c), _C.ptr(s.cnt_c[0:1]),
+                                                   _C.ptr(s.cnt_c[1:2]), _C.ptr(s.ws_compact), st), 'compacted_coord')
+            s.ready = torch.cuda.Event(); s.ready.record(self.aux)
+        s.rays = (rays_o, rays_d)                      # keep the tensors alive until the kernels ran
+
+    # ------------------------------------------------------------------ one training step
+    def step(self, rays_o, rays_d, target, bg, next_rays=None):
+        """Trains on (rays_o, rays_d, target, bg). next_rays = (rays_o, rays_d) of the FOLLOWING call (optional): their march starts now, on the aux
+        stream, and overlaps this step's field kernels and gradient exchange. Returns the loss as a 0-dim device tensor (no sync)."""
         f = self.f
-        self.counter.zero_(); self.cnt_c.zero_()
-        rm.rays_sampler_api(rays_o, rays_d, self.bitfield, None, None, None, self.aabb[0], self.aabb[1], self.near, self.cone, self.coords, self.rays_index, self.numsteps, self.counter)
-        # the reference's no-grad pre-pass over ALL samples (ngp_grid_sampler.py:229-230) feeds only compacted_coord's dead transmittance loop
-        # (compacted_coord.cu:41-44): skipping it changes no result
-        self.coords_c.zero_()
-        rm.compacted_coord_api(None, self.coords, self.numsteps, None, self.rgb_act, self.dens_act, self.aabb[0], self.aabb[1], self.coords_c, self.numsteps_c, self.cnt_c[0:1], self.cnt_c[1:2])
-        n_rows = self.T
-        pp, dp = _C.rows(self.coords_c[:, :3])[0], _C.rows(self.coords_c[:, 4:])[0]
-        _C.check(_C.lib.xrb_ngp_mlp_forward(f.cfg, f.tab, _C.ptr(f._dens16), _C.ptr(f._color16), _C.ptr(f._image), pp, 7, dp, 7, n_rows, _C.ptr(self.raw), 1, _C.stream()), 'field fwd')
-        rm.calc_rgb_forward_api(self.raw, self.coords_c, self.numsteps, self.numsteps_c, bg, self.rgb_act, self.dens_act, 0.0, 1.0, self.rgb)
-        loss, g = huber5_grad(self.rgb, target)
-        self.draw.zero_()
-        rm.calc_rgb_backward_api(self.raw, self.numsteps_c, self.coords_c, g, self.rgb, self.grid_mean, self.rgb_act, self.dens_act, 0.0, 1.0, self.draw)
-        self.grads.zero_()
-        gv = self.grads.views
-        _C.check(_C.lib.xrb_ngp_mlp_backward(f.cfg, f.tab, _C.ptr(f._dens16), _C.ptr(f._color16), pp, 7, dp, 7,
-                                             _C.ptr(self.draw), n_rows, _C.ptr(gv[0]), _C.ptr(gv[1]), _C.ptr(gv[2]), _C.stream()), 'field bwd')
-        div = self.grads.allreduce(self.group)
+        s = self.slots[self.cur]
+        if s.ready is None or s.rays is None or s.rays[0].data_ptr() != _ptr_of(rays_o):
+            self._prepare(self.cur, rays_o, rays_d)
+        if next_rays is not None:
+            self._prepare(self.cur ^ 1, *next_rays)
+        main = torch.cuda.current_stream()
+        main.wait_event(s.ready)
+        st = _C.stream()
+        n_rows_dev = _C.ptr(s.cnt_c[1:2])
+        pp, dp = _C.rows(s.coords_c[:, :3])[0], _C.rows(s.coords_c[:, 4:])[0]
+        _C.check(_C.lib.xrb_ngp_mlp_forward(f.cfg, f.tab, _C.ptr(f._dens16), _C.ptr(f._color16), _C.ptr(f._image), pp, 7, dp, 7, self.T, n_rows_dev, _C.ptr(self.raw), 1, st), 'field fwd')
+        _C.check(_C.lib.xrb_rm_calc_rgb_forward(_C.ptr(self.raw), _C.ptr(s.coords_c), _C.ptr(s.numsteps), _C.ptr(s.numsteps_c), _C.f32(bg), self.n_rays, self.rgb_act, self.dens_act,
+                                                _C.ptr(self.rgb), st), 'calc_rgb_forward')
+        self.loss_accum.zero_()
+        _C.check(_C.lib.xrb_ngp_huber5_grad(_C.ptr(self.rgb), _C.f32(target), self.n_rays * 3, 0.1, _C.ptr(self.grad_rgb), _C.ptr(self.loss_accum), st), 'huber5')
+        # rows of dL/draw beyond the compacted count are never read (n_rows_dev); rows owned by rays are all written by the kernel
+        _C.check(_C.lib.xrb_rm_calc_rgb_backward(_C.ptr(self.raw), _C.ptr(s.numsteps_c), _C.ptr(s.coords_c), _C.ptr(self.grad_rgb), _C.ptr(self.rgb), _C.ptr(self.grid_mean), self.n_rays,
+                                                 self.rgb_act, self.dens_act, _C.ptr(self.draw), st), 'calc_rgb_backward')
+        self.gflat.zero_()
+        if self.bwd_impl == 1:
+            _C.check(_C.lib.xrb_ngp_mlp_backward_tc(f.cfg, f.tab, _C.ptr(f._image), pp, 7, dp, 7, _C.ptr(self.draw), self.T, n_rows_dev, _C.ptr(self.g_hash), _C.ptr(self.g_dens),
+                                                    _C.ptr(self.g_color), st), 'field bwd (tcgen05)')
+        else:
+            n_rows = int(s.cnt_c[1].item())           # the CUDA-core kernel has no device-side count: one sync (comparator path only)
+            _C.check(_C.lib.xrb_ngp_mlp_backward(f.cfg, f.tab, _C.ptr(f._dens16), _C.ptr(f._color16), pp, 7, dp, 7, _C.ptr(self.draw), n_rows, _C.ptr(self.g_hash), _C.ptr(self.g_dens),
+                                                 _C.ptr(self.g_color), st), 'field bwd')
+        s.free = torch.cuda.Event(); s.free.record(main)
         self.step_n += 1
-        shadows = [f._table16, f._dens16, f._color16]
         it = self.step_n - 1                                                            # runner.iter inside after_train_iter
         mom = 0.0 if self.ema_momentum is None else min(self.ema_momentum, (1 + it) / (self.ema_warm_up + it))
-        for p, p16, g_, m, v, e in zip(self.params, shadows, gv, self.m, self.v, self.ema):
-            _C.check(_C.lib.xrb_adam_ema_step(_C.ptr(p.data), _C.ptr(p16), _C.ptr(g_), _C.ptr(m), _C.ptr(v), p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                                              self.step_n, div, _C.ptr(e), mom, _C.stream()), 'adam')
+        self._exchange_and_update(mom)
         _C.check(_C.lib.xrb_ngp_pack_weights(f.cfg, _C.ptr(f.density_params.data), _C.ptr(f.color_params.data), _C.ptr(f._image), _C.stream()), 'pack')
         f.rebuild_cells()                                                               # the fp16 table changed: refresh its cell image
         f._ver = (f.hash_params._version, f.density_params._version, f.color_params._version, f.hash_params.device)  # shadows are current
-        return loss
+        self.cur ^= 1
+        return self.loss_accum[0]
+
+    def _adam(self, p, p16, g, m, v, e, mom, div, bf16=False):
+        fn = _C.lib.xrb_adam_ema_step_bf16grad if bf16 else _C.lib.xrb_adam_ema_step
+        _C.check(fn(_C.ptr(p), _C.ptr(p16), _C.ptr(g), _C.ptr(m), _C.ptr(v), p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_n, div, _C.ptr(e), mom,
+                    _C.stream()), 'adam')
+
+    def _exchange_and_update(self, mom):
+        import torch.distributed as dist
+        f = self.f
+        if self.grad_comm == 'sharded':
+            ex = self.ex
+            _C.check(_C.lib.xrb_pack_bf16(_C.ptr(self.gflat[:ex.padded]), _C.ptr(self.g16), ex.padded, _C.stream()), 'pack_bf16')
+            ex.reduce_scatter_sum(self.g16, self.g16_mine)
+            dist.all_reduce(self.g_mlp, op=dist.ReduceOp.SUM, group=self.group)
+            b, e = ex.begin, ex.end
+            if e > b:
+                self._adam(f.hash_params.data[b:e], self.t16_pad[b:e], self.g16_mine[:e - b], self.m[0], self.v[0], self.ema[0], mom, float(self.world), bf16=True)
+            ex.all_gather(self.t16_pad, self.t16_pad[self.rank * ex.per:(self.rank + 1) * ex.per])
+            f._table16.copy_(self.t16_pad[:ex.n])
+            self.master_stale = True
+            self._adam(f.density_params.data, f._dens16, self.g_dens, self.m[1], self.v[1], self.ema[1], mom, float(self.world))
+            self._adam(f.color_params.data, f._color16, self.g_color, self.m[2], self.v[2], self.ema[2], mom, float(self.world))
+            return
+        div = 1.0
+        if self.grad_comm == 'allreduce':
+            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.group)
+            div = float(self.world)
+        shadows = [f._table16, f._dens16, f._color16]
+        for p, p16, g_, m, v, e in zip(self.params, shadows, self.grads, self.m, self.v, self.ema):
+            self._adam(p.data, p16, g_, m, v, e, mom, div)
+
+    # ------------------------------------------------------------------ bookkeeping
+    def trained_rays(self, slot=None):
+        """rays of the last step whose EVERY marched sample took part in the step (numsteps_c.count == numsteps.count): 0-dim device tensor"""
+        s = self.slots[self.cur ^ 1 if slot is None else slot]
+        return (s.numsteps_c[:, 0] == s.numsteps[:, 0]).sum()
+
+    def compacted_samples(self, slot=None):
+        return self.slots[self.cur ^ 1 if slot is None else slot].cnt_c[1]
+
+    def sync_master(self):
+        """sharded mode: fetch the other ranks' slices of the fp32 master table (and EMA) so that state_dict() / EMA swaps see whole tensors"""
+        if self.grad_comm != 'sharded' or not self.master_stale:
+            return
+        ex, f = self.ex, self.f
+        full = torch.zeros(ex.padded, dtype=torch.float32, device=self.dev)
+        mine = torch.zeros(ex.per, dtype=torch.float32, device=self.dev)
+        mine[:ex.end - ex.begin].copy_(f.hash_params.data[ex.begin:ex.end])
+        ex.all_gather(full, mine)
+        f.hash_params.data.copy_(full[:ex.n])
+        self.master_stale = False
+
+    def ema_full(self):
+        """EMA of the hash table as one tensor (sharded mode gathers the slices)"""
+        if self.ema[0] is None:
+            return None
+        if self.grad_comm != 'sharded':
+            return self.ema[0]
+        ex = self.ex
+        full = torch.zeros(ex.padded, dtype=torch.float32, device=self.dev)
+        mine = torch.zeros(ex.per, dtype=torch.float32, device=self.dev)
+        mine[:ex.end - ex.begin].copy_(self.ema[0])
+        ex.all_gather(full, mine)
+        return full[:ex.n]
+
+
+def _ptr_of(t):
+    return t.data_ptr() if t.is_contiguous() else -1
