@@ -1,29 +1,21 @@
-"""Summarise an ncu launch list (ncu --metrics gpu__time_duration.sum --csv --log-file X.csv) into a markdown table: per kernel launches / mean / total / share."""
-import collections
+"""ncu launch list (csv from `ncu --metrics gpu__time_duration.sum --clock-control none --csv`) -> per-kernel table.  python scripts/launch_list.py launches.csv [title]"""
 import csv
 import sys
+from collections import OrderedDict
 
-
-def main(path, out, title):
-    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
-    hdr = next(r for r in rows if 'Kernel Name' in r)
-    start = rows.index(hdr)
-    ki, vi = hdr.index('Kernel Name'), hdr.index('Metric Value')
-    agg = collections.OrderedDict()
-    for r in rows[start + 1:]:
-        if len(r) <= vi:
-            continue
-        a = agg.setdefault(r[ki], [0, 0.0])
-        a[0] += 1; a[1] += float(r[vi].replace(',', '')) / 1e3          # ns -> us
-    tot = sum(t for _, t in agg.values())
-    with open(out, 'w') as fh:
-        fh.write(f'# {title}\n\nsource: `{path}`; per-launch times are cold-cache and serialised by ncu - use the SHARES.\n\n| kernel | launches | mean us | total us | share |\n|---|---|---|---|---|\n')
-        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            if t / tot < 0.001:
-                continue
-            name = k.split('(')[0].replace('void ', '')[:70]
-            fh.write(f'| `{name}` | {n} | {t / n:.1f} | {t:.1f} | {100 * t / tot:.1f} % |\n')
-
-
-if __name__ == '__main__':
-    main(sys.argv[1], sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else 'launch list')
+rows = list(csv.reader(l for l in open(sys.argv[1], errors='replace') if l.startswith('"')))
+hdr = rows[0]
+ki, vi, ui = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
+agg = OrderedDict()
+for r in rows[1:]:
+    if len(r) <= vi:
+        continue
+    v = float(r[vi].replace(',', ''))
+    v = v / 1e3 if r[ui] in ('ns', 'nsecond') else (v * 1e3 if r[ui] in ('ms', 'msecond') else v)
+    a = agg.setdefault(r[ki][:70], [0, 0.0])
+    a[0] += 1; a[1] += v
+tot = sum(a[1] for a in agg.values())
+print('# %s\n' % (sys.argv[2] if len(sys.argv) > 2 else sys.argv[1]))
+print('| kernel | launches | mean us | total us | share |\n|---|---|---|---|---|')
+for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print('| `%s` | %d | %.1f | %.1f | %.1f %% |' % (k, c, t / c, t, 100 * t / tot))

@@ -158,22 +158,24 @@ __global__ void __launch_bounds__(128) mlp_forward_simt_kernel(const __half *__r
 }
 
 // ---------------------------------------------------------------------------- tensor-core field (impl 1)
-constexpr int TC_WG = 2;                 // warpgroups (= concurrent 128-sample tiles) per CTA
-constexpr uint32_t TC_TMEM_COLS = 128;   // 64 fp32 accumulator columns per warpgroup
-
-// MAXREG: 128 -> 2 CTAs/SM (16 warps); 80 -> 3 CTAs/SM (24 warps, ~70 B of spills): the gather is latency-bound, occupancy wins
-// NP: static gather plan (ngp_field.cuh plan_mode): 0 = per-level form decided at run time, >0 = levels [0,NP) from the cell image, the rest hashed
-template <bool DENSITY_ONLY, int MAXREG, int NP>
-__global__ void __maxnreg__(MAXREG) ngp_field_tc_kernel(HashGridDev g, const __half2 *__restrict__ table, const uint8_t *__restrict__ cells, const void *__restrict__ weight_image, uint32_t image_bytes,
-                                                                      int density_hidden, int color_hidden, const float *__restrict__ pts, int pts_stride,
-                                                                      const float *__restrict__ dirs, int dirs_stride, int n, const int32_t *__restrict__ n_dev, float *__restrict__ out) {
+// NWG warpgroups (= concurrent 128-sample tiles) per CTA share ONE resident weight image; 64 fp32 accumulator columns of TMEM each.
+// The gather is latency-bound (ncu: 69 % of the stall samples are long-scoreboard, issue 32 %, L1 65 %, L2 45 %), so the shapes trade registers per
+// thread for warps per SM:   <2,96> / <2,128>: two CTAs per SM (16 warps);  <6,80>: one CTA per SM, 24 warps;  <8,64>: one CTA per SM, 32 warps.
+// NP: static gather plan (ngp_field.cuh plan_mode): 0 = per-level form decided at run time, >0 = levels [0,NP) from the cell image, the rest hashed.
+// dbg (developer ablation, XRB_FIELD_DBG): 1 = no gather (encoding := position bits), 2 = no MLP layers.
+template <bool DENSITY_ONLY, int NWG, int MAXREG, int NP>
+__global__ void __launch_bounds__(128 * NWG, NWG == 2 ? 2 : 1) __maxnreg__(MAXREG)
+ngp_field_tc_kernel(HashGridDev g, const __half2 *__restrict__ table, const uint8_t *__restrict__ cells, const void *__restrict__ weight_image, uint32_t image_bytes, int density_hidden,
+                    int color_hidden, const float *__restrict__ pts, int pts_stride, const float *__restrict__ dirs, int dirs_stride, int n, const int32_t *__restrict__ n_dev,
+                    float *__restrict__ out, int dbg) {
     extern __shared__ uint8_t dyn_smem[];
     if (n_dev) n = min(n, max(*n_dev, 0));
-    TcWarpgroup c = tc_cta_setup<TC_WG, TC_TMEM_COLS>(dyn_smem, weight_image, image_bytes);
+    constexpr uint32_t TMEM_COLS = NWG <= 2 ? 128 : (NWG <= 4 ? 256 : 512);
+    TcWarpgroup c = tc_cta_setup<NWG, TMEM_COLS>(dyn_smem, weight_image, image_bytes);
     const uint32_t tmem_base = c.tmem - c.wg * 64;
     const WeightImageLayout L = weight_image_layout(density_hidden, color_hidden);
     const int n_tiles = (n + 127) / 128;
-    for (int tile = blockIdx.x * TC_WG + c.wg; tile < n_tiles; tile += gridDim.x * TC_WG) {
+    for (int tile = blockIdx.x * NWG + c.wg; tile < n_tiles; tile += gridDim.x * NWG) {
         const int i = tile * 128 + c.row;
         const bool valid = i < n;
         float x = 0.5f, y = 0.5f, z = 0.5f, dx = 0.5f, dy = 0.5f, dz = 0.5f;
@@ -181,16 +183,27 @@ __global__ void __maxnreg__(MAXREG) ngp_field_tc_kernel(HashGridDev g, const __h
             const float *p = pts + (size_t)i * pts_stride; x = p[0]; y = p[1]; z = p[2];
             if (!DENSITY_ONLY) { const float *d = dirs + (size_t)i * dirs_stride; dx = d[0]; dy = d[1]; dz = d[2]; }
         }
-        if (DENSITY_ONLY) {
-            float dout[16];
+        float dout[16];
+        if (dbg & 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a_store_chunk(c, q, make_uint4(pack_h2(x, y), pack_h2(z, x), pack_h2(y, z), pack_h2(x, z)));
+            if (dbg & 2) { for (int k = 0; k < 16; ++k) dout[k] = x; } else tc_density_from_a(c, L, density_hidden, dout);
+        } else if (dbg & 2) {
+            float acc = 0.f;
+#pragma unroll
+            for (int l = 0; l < 16; ++l) { float2 f = hash_level(table, cells, g, l, x, y, z, plan_mode<NP>(l)); acc += f.x + f.y; }
+            for (int k = 0; k < 16; ++k) dout[k] = acc;
+        } else {
             tc_density<NP>(c, L, density_hidden, table, cells, g, x, y, z, dout);
+        }
+        if (DENSITY_ONLY) {
             if (valid) out[i] = dout[0];
         } else {
-            float4 raw = tc_field<NP>(c, L, density_hidden, color_hidden, table, cells, g, x, y, z, dx, dy, dz);
+            float4 raw = (dbg & 2) ? make_float4(dout[0], dout[1], dout[2], dout[3]) : tc_color_from_density(c, L, color_hidden, dout, dx, dy, dz);
             if (valid) reinterpret_cast<float4 *>(out)[i] = raw;
         }
     }
-    tc_cta_teardown<TC_TMEM_COLS>(tmem_base);
+    tc_cta_teardown<TMEM_COLS>(tmem_base);
 }
 
 static int persistent_grid(const void *kernel, int block, size_t smem, int work_ctas, int min_per_sm = 1) {
@@ -330,28 +343,32 @@ int launch_field(const xrb_ngp_config *cfg, const xrb_ngp_table *tab, const void
                                                                  dirs, dirs_stride, n, n_dev, out);
     } else {
         uint32_t image_bytes = weight_image_layout(cfg->density_hidden, cfg->color_hidden).total;
-        size_t smem = tc_cta_smem_bytes<TC_WG>(image_bytes);
-        // register budget of the field kernel: 128 -> 2 CTAs/SM using the whole register file; 96 -> 2 CTAs/SM leaving 16K registers per SM
-        // for the (latency-bound, 36-register) march kernel of the NEXT batch to co-reside on another stream.
-        static const int variant = getenv("XRB_TC_REGS") ? atoi(getenv("XRB_TC_REGS")) : 96;
-        const int regs = variant == 128 ? 128 : 96;
-        // static gather plan: the kernel is specialised for "levels [0,NP) packed, all others hashed" (NP = 6, 7, 12); anything else takes the run-time form
+        // kernel shape (see ngp_field_tc_kernel): XRB_TC_SHAPE = 0 <2 WG,96 regs> (leaves 16K registers per SM for the march kernel of the NEXT batch to co-reside on
+        // another stream), 1 <2,128>, 2 <6,80>, 3 <8,64>
+        static const int shape = getenv("XRB_TC_SHAPE") ? atoi(getenv("XRB_TC_SHAPE")) : (getenv("XRB_TC_REGS") && atoi(getenv("XRB_TC_REGS")) == 128 ? 1 : 0);
+        static const int dbg = getenv("XRB_FIELD_DBG") ? atoi(getenv("XRB_FIELD_DBG")) : 0;
+        // static gather plan: the kernel is specialised for "levels [0,NP) packed, all others hashed" (NP = 6, 7); anything else takes the run-time form
         const int npl = tab->n_packed_levels;
-        const int np = (plan_valid(g, npl) && (npl == 6 || npl == 7 || npl == 12)) ? npl : 0;
+        const int np = (plan_valid(g, npl) && (npl == 6 || npl == 7)) ? npl : 0;
         int n_tiles = (n + 127) / 128;
-#define XRB_LAUNCH_TC(D, R, NP)                                                                                                                     \
+#define XRB_LAUNCH_TC(D, NWG, R, NP)                                                                                                                \
     do {                                                                                                                                            \
-        auto k = ngp_field_tc_kernel<D, R, NP>;                                                                                                     \
+        auto k = ngp_field_tc_kernel<D, NWG, R, NP>;                                                                                                \
+        const size_t smem = tc_cta_smem_bytes<NWG>(image_bytes);                                                                                    \
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                                                            \
-        int grid = persistent_grid((const void *)k, 128 * TC_WG, smem, (n_tiles + TC_WG - 1) / TC_WG, 2);                                           \
-        k<<<grid, 128 * TC_WG, smem, s>>>(g, (const __half2 *)table, cells, image, image_bytes, cfg->density_hidden, cfg->color_hidden, pts, pts_stride, dirs, dirs_stride, n, n_dev, out); \
+        int grid = persistent_grid((const void *)k, 128 * NWG, smem, (n_tiles + NWG - 1) / NWG, NWG == 2 ? 2 : 1);                                  \
+        k<<<grid, 128 * NWG, smem, s>>>(g, (const __half2 *)table, cells, image, image_bytes, cfg->density_hidden, cfg->color_hidden, pts, pts_stride, dirs, dirs_stride, n, n_dev, out, dbg); \
     } while (0)
-#define XRB_LAUNCH_TC_NP(D, R)                                                                                                                      \
+#define XRB_LAUNCH_TC_NP(D, NWG, R)                                                                                                                 \
     do {                                                                                                                                            \
-        if (np == 6) XRB_LAUNCH_TC(D, R, 6); else if (np == 7) XRB_LAUNCH_TC(D, R, 7); else if (np == 12) XRB_LAUNCH_TC(D, R, 12); else XRB_LAUNCH_TC(D, R, 0); \
+        if (np == 6) XRB_LAUNCH_TC(D, NWG, R, 6); else if (np == 7) XRB_LAUNCH_TC(D, NWG, R, 7); else XRB_LAUNCH_TC(D, NWG, R, 0);                   \
     } while (0)
-        if (density_only) { if (regs == 128) XRB_LAUNCH_TC_NP(true, 128); else XRB_LAUNCH_TC_NP(true, 96); }
-        else { if (regs == 128) XRB_LAUNCH_TC_NP(false, 128); else XRB_LAUNCH_TC_NP(false, 96); }
+#define XRB_LAUNCH_TC_SHAPE(D)                                                                                                                      \
+    do {                                                                                                                                            \
+        if (shape == 1) XRB_LAUNCH_TC_NP(D, 2, 128); else if (shape == 2) XRB_LAUNCH_TC_NP(D, 6, 80); else if (shape == 3) XRB_LAUNCH_TC_NP(D, 8, 64); else XRB_LAUNCH_TC_NP(D, 2, 96); \
+    } while (0)
+        if (density_only) XRB_LAUNCH_TC_SHAPE(true); else XRB_LAUNCH_TC_SHAPE(false);
+#undef XRB_LAUNCH_TC_SHAPE
 #undef XRB_LAUNCH_TC_NP
 #undef XRB_LAUNCH_TC
     }
