@@ -156,6 +156,14 @@ int xrb_tcnn_sh4_forward(const float *dirs, int dir_stride, int n, void *out_fp1
 /* tcnn.Network(FullyFusedMLP).forward, SIMT reference-grade implementation: x fp16[n,in_w] -> y fp16[n,16] */
 int xrb_tcnn_mlp_forward(const void *params_fp16, const void *x_fp16, int n, int in_w, int width, int n_hidden, void *y_fp16, void *stream);
 
+/* Backward of the two stand-alone modules (what `tinycudann`'s autograd bindings give the reference when it trains through them,
+ * hashnerf_mlp.py:36-45,:60-77): d_enc fp16[n,32] (x grad_scale) -> fp32 table gradient (ACCUMULATED); and for the MLP x fp16[n,32],
+ * dy fp16[n,16] -> dx fp16[n,32] (may be NULL) + fp32 parameter gradient (ACCUMULATED, tcnn layout). CUDA-core kernels: the training hot path
+ * is the fused field (xrb_ngp_mlp_backward_tc); these exist so that the composable modules are trainable. */
+int xrb_tcnn_hashgrid_backward(const xrb_ngp_config *cfg, const float *x, int x_stride, int n, const void *d_enc_fp16, float grad_scale, float *d_table, void *stream);
+int xrb_tcnn_mlp_backward(const void *params_fp16, const void *x_fp16, const void *dy_fp16, int n, int in_w, int width, int n_hidden, void *dx_fp16, float *d_params,
+                          void *stream);
+
 /* HashNerfMLP.run_mlp (hashnerf_mlp.py:55-79) fused: pts/dirs f32 rows (stride in floats, so `coords[:, :3]` /
  * `coords[:, 4:]` views of a [S,7] buffer work in place) -> raw f32[n,4] = (rgb3, density1).
  * impl: 0 = SIMT (CUDA cores), 1 = tcgen05 tensor-core tiles (weights from `weight_image`).

@@ -218,3 +218,39 @@ def test_adam_ema_step_matches_torch_and_mmcv_ema_rule():
         _C.check(_C.lib.xrb_adam_ema_step(_C.ptr(p), None, _C.ptr(g * (1 + 0.1 * step)), _C.ptr(m), _C.ptr(v), n, 1e-2, 0.9, 0.99, 1e-15, 1e-6, step, 1.0, _C.ptr(ema), mom, _C.stream()))
     assert torch.allclose(p, ref.detach(), rtol=1e-5, atol=1e-6)
     assert torch.allclose(ema, ema_ref, rtol=1e-5, atol=1e-6)
+
+
+def test_tcnn_modules_train_like_the_fused_field(field_and_weights):
+    """The reference's HashNerfMLP.run_mlp (hashnerf_mlp.py:55-79) written against `xrnerf_b200.tcnn` exactly as it is written against tinycudann, under
+    torch.autograd: the parameter gradients of the four composable modules equal the fused field's backward (same arithmetic; fp16 activation gradients between
+    the modules, as tcnn's bindings have): 5e-3 relative L2, 1e-2 of max per vector. Flat-parameter import/export feeds the modules."""
+    import xrnerf_b200.tcnn as tcnn
+    from xrnerf_b200.ngp import PER_LEVEL_SCALE
+    f, table, dens, color = field_and_weights
+    enc = tcnn.Encoding(3, dict(otype='HashGrid', n_levels=16, n_features_per_level=2, log2_hashmap_size=19, base_resolution=16, per_level_scale=PER_LEVEL_SCALE)).cuda()
+    sh = tcnn.Encoding(3, dict(otype='SphericalHarmonics', degree=4)).cuda()
+    dnet = tcnn.Network(32, 16, dict(otype='FullyFusedMLP', activation='ReLU', output_activation='None', n_neurons=64, num_layers=1)).cuda()
+    cnet = tcnn.Network(31, 3, dict(otype='FullyFusedMLP', activation='ReLU', output_activation='None', n_neurons=64, num_layers=2)).cuda()
+    enc.import_params(dev(table)); dnet.import_params(dev(dens)); cnet.import_params(dev(color))
+    assert torch.equal(enc.export_params(), dev(table)) and torch.equal(cnet.export_params(), dev(color))
+    n = 6000
+    pts, dirs = _pts(n, seed=33)
+    rng = np.random.default_rng(4)
+    draw = dev((rng.normal(0, 1, (n, 4)) * 0.05).astype(np.float32))     # large enough for fp16 activation gradients
+    h = enc(dev(pts))
+    d_out = dnet(h)
+    c_out = cnet(torch.cat([d_out[..., 1:], sh(dev(dirs))], dim=-1))
+    out = torch.cat([c_out, d_out[..., :1]], -1).to(torch.float32).contiguous()
+    raw_fused = f.run_mlp(dev(pts), dev(dirs), impl=0)
+    assert float((out - raw_fused).abs().max()) <= 2e-3 + 1e-2 * float(raw_fused.abs().max())
+    (out * draw).sum().backward()
+    dt, dd, dc = f.backward_params(dev(pts), dev(dirs), draw, impl=0)
+    for name, a, b in (('table', enc.params.grad, dt), ('density', dnet.params.grad, dd), ('color', cnet.params.grad, dc)):
+        assert a is not None and a.dtype == torch.float32 and a.shape == b.shape
+        err = (a - b).abs()
+        assert float(torch.sqrt((err.double() ** 2).sum() / (b.double() ** 2).sum())) <= 5e-3, name
+        assert float(err.max()) <= 1e-2 * float(b.abs().max()), (name, float(err.max()), float(b.abs().max()))
+    # one optimiser step through the modules changes their output (they are trainable end to end)
+    opt = torch.optim.Adam([enc.params, dnet.params, cnet.params], lr=1e-2)
+    opt.step()
+    assert not torch.equal(enc(dev(pts)), h.detach())

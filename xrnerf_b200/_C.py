@@ -62,6 +62,8 @@ _SIGS = {
     'xrb_tcnn_hashgrid_forward': (_i, [_cfg, _tab, P, _i, _i, P, P]),
     'xrb_tcnn_sh4_forward': (_i, [P, _i, _i, P, P]),
     'xrb_tcnn_mlp_forward': (_i, [P, P, _i, _i, _i, _i, P, P]),
+    'xrb_tcnn_hashgrid_backward': (_i, [_cfg, P, _i, _i, P, _f, P, P]),
+    'xrb_tcnn_mlp_backward': (_i, [P, P, P, _i, _i, _i, _i, P, P, P]),
     'xrb_ngp_mlp_forward': (_i, [_cfg, _tab, P, P, P, P, _i, P, _i, _i, P, P, _i, P]),
     'xrb_ngp_density_forward': (_i, [_cfg, _tab, P, P, P, _i, _i, P, _i, P]),
     'xrb_ngp_mlp_backward': (_i, [_cfg, _tab, P, P, P, _i, P, _i, P, _i, P, P, P, P]),

@@ -288,6 +288,119 @@ __global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ p, __half
     }
 }
 
+// ---------------------------------------------------------------------------- backward of the stand-alone tcnn-shaped modules (xrnerf_b200/tcnn.py autograd)
+// tcnn.Encoding(HashGrid).backward: dL/d enc fp16[n,32] -> fp32 table gradient (+=). thread = (sample, level) like hashgrid_forward_kernel.
+__global__ void __launch_bounds__(256) hashgrid_backward_kernel(HashGridDev g, const float *__restrict__ x, int x_stride, int n, const __half2 *__restrict__ d_enc, float scale,
+                                                                float *__restrict__ d_table) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t i = t >> 4; int l = (int)(t & 15);
+    if (i >= n) return;
+    const float *p = x + (size_t)i * x_stride;
+    const float2 gy = __half22float2(d_enc[(size_t)i * 16 + l]);
+    const float g0 = gy.x * scale, g1 = gy.y * scale;
+    if (g0 == 0.f && g1 == 0.f) return;
+    const uint32_t hs = g.offset[l + 1] - g.offset[l], res = g.res[l];
+    float2 *tl = reinterpret_cast<float2 *>(d_table) + g.offset[l];
+    const float sc = g.scale[l];
+    float qx = __fmaf_rn(sc, p[0], 0.5f), qy = __fmaf_rn(sc, p[1], 0.5f), qz = __fmaf_rn(sc, p[2], 0.5f);
+    int ixs, iys, izs;
+    float fx = floor_small(qx, &ixs), fy = floor_small(qy, &iys), fz = floor_small(qz, &izs);
+    const uint32_t ix = (uint32_t)ixs, iy = (uint32_t)iys, iz = (uint32_t)izs;
+    fx = qx - fx; fy = qy - fy; fz = qz - fz;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float w = ((c & 1) ? fx : 1.f - fx) * ((c & 2) ? fy : 1.f - fy) * ((c & 4) ? fz : 1.f - fz);
+        uint32_t idx = grid_index(ix + (c & 1), iy + ((c >> 1) & 1), iz + ((c >> 2) & 1), hs, res);
+        atomicAdd(tl + idx, make_float2(w * g0, w * g1));
+    }
+}
+
+void launch_hashgrid_backward(const HashGridDev &g, const float *x, int x_stride, int n, const void *d_enc, float scale, float *d_table, cudaStream_t s) {
+    int64_t threads = (int64_t)n * 16;
+    hashgrid_backward_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(g, x, x_stride, n, (const __half2 *)d_enc, scale, d_table);
+}
+
+// tcnn.Network(FullyFusedMLP).backward: x fp16[n,32], dy fp16[n,16] -> dx fp16[n,32] (optional), fp32 parameter gradient (+=). Same structure as the density half of
+// ngp_field_bwd_kernel: forward recompute with the layer inputs parked in shared memory, per-thread dX, block GEMM dW with register accumulators.
+template <int NH>
+__global__ void __launch_bounds__(BW_THREADS) tcnn_mlp_bwd_kernel(const __half *__restrict__ params, const __half *__restrict__ x, const __half *__restrict__ dy, int n,
+                                                                  __half *__restrict__ dx, float *__restrict__ d_params) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    constexpr int NPAR = 64 * 32 + (NH - 1) * 64 * 64 + 16 * 64;
+    __half *p = reinterpret_cast<__half *>(smem_raw);
+    __half *W = p; p += NPAR;
+    __half *X = p; p += 128 * 32;
+    __half *H[NH]; for (int k = 0; k < NH; ++k) { H[k] = p; p += 128 * 64; }
+    __half *DY = p; p += 128 * 64;
+    for (int k = threadIdx.x; k < NPAR; k += BW_THREADS) W[k] = params[k];
+    float a_in[16] = {0}, a_hid[NH > 1 ? (NH - 1) * 32 : 1] = {0}, a_out[8] = {0};
+    __syncthreads();
+    const int n_tiles = (n + 127) / 128;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int i = tile * 128 + threadIdx.x;
+        const bool valid = i < n;
+        const int n_valid = min(128, n - tile * 128);
+        {
+            uint4 *dst = reinterpret_cast<uint4 *>(X + (size_t)threadIdx.x * 32);
+            const uint4 *src = reinterpret_cast<const uint4 *>(x + (size_t)i * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = valid ? src[q] : make_uint4(0, 0, 0, 0);
+        }
+        float h[64];
+        fwd_layer_smem<32, 64, true>(W, X + (size_t)threadIdx.x * 32, h);
+        store_row_h(H[0] + (size_t)threadIdx.x * 64, h, 64);
+#pragma unroll
+        for (int k = 1; k < NH; ++k) { fwd_layer_smem<64, 64, true>(W + 64 * 32 + (k - 1) * 64 * 64, H[k - 1] + (size_t)threadIdx.x * 64, h); store_row_h(H[k] + (size_t)threadIdx.x * 64, h, 64); }
+        float gy[64], gx[64];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) gy[k] = valid ? __half2float(dy[(size_t)i * 16 + k]) : 0.f;
+        stage_dy(DY, gy, 16);
+        __syncthreads();
+        dw_accumulate<64, 16, 2, 4>(DY, H[NH - 1], a_out, n_valid);
+        bwd_layer_dx<64, 16>(W + 64 * 32 + (NH - 1) * 64 * 64, gy, gx);
+        __syncthreads();
+#pragma unroll
+        for (int k = NH - 1; k >= 1; --k) {
+            const __half *act = H[k] + (size_t)threadIdx.x * 64;
+#pragma unroll
+            for (int q = 0; q < 64; ++q) gy[q] = __half2float(act[q]) > 0.f ? gx[q] : 0.f;
+            stage_dy(DY, gy, 64);
+            __syncthreads();
+            dw_accumulate<64, 64, 4, 8>(DY, H[k - 1], a_hid + (k - 1) * 32, n_valid);
+            bwd_layer_dx<64, 64>(W + 64 * 32 + (k - 1) * 64 * 64, gy, gx);
+            __syncthreads();
+        }
+        {
+            const __half *act = H[0] + (size_t)threadIdx.x * 64;
+#pragma unroll
+            for (int q = 0; q < 64; ++q) gy[q] = __half2float(act[q]) > 0.f ? gx[q] : 0.f;
+            stage_dy(DY, gy, 64);
+            __syncthreads();
+            dw_accumulate<32, 64, 4, 4>(DY, X, a_in, n_valid);
+            bwd_layer_dx<32, 64>(W, gy, gx);
+            __syncthreads();
+        }
+        if (dx && valid) store_row_h(dx + (size_t)i * 32, gx, 32);
+    }
+    dw_flush<32, 64, 4, 4>(a_in, d_params);
+#pragma unroll
+    for (int k = 1; k < NH; ++k) dw_flush<64, 64, 4, 8>(a_hid + (k - 1) * 32, d_params + 64 * 32 + (k - 1) * 64 * 64);
+    dw_flush<64, 16, 2, 4>(a_out, d_params + 64 * 32 + (NH - 1) * 64 * 64);
+}
+
+template <int NH>
+static int launch_tcnn_mlp_bwd(const void *params, const void *x, const void *dy, int n, void *dx, float *d_params, cudaStream_t s) {
+    constexpr int NPAR = 64 * 32 + (NH - 1) * 64 * 64 + 16 * 64;
+    size_t smem = sizeof(__half) * ((size_t)NPAR + 128 * 32 + (size_t)NH * 128 * 64 + 128 * 64);
+    auto k = tcnn_mlp_bwd_kernel<NH>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, BW_THREADS, smem); if (per_sm < 1) per_sm = 1;
+    int dev = 0, sms = NUM_SMS; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int n_tiles = (n + 127) / 128, grid = sms * per_sm; if (grid > n_tiles) grid = n_tiles; if (grid < 1) grid = 1;
+    k<<<grid, BW_THREADS, smem, s>>>((const __half *)params, (const __half *)x, (const __half *)dy, n, (__half *)dx, d_params);
+    return check_launch("tcnn_mlp_backward");
+}
+
 // fp32 gradient -> bf16 (the wire format of the sharded data-parallel step: reduce-scatter in bf16, see xrnerf_b200/train.py)
 __global__ void __launch_bounds__(256) pack_bf16_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int64_t n) {
     int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -340,6 +453,33 @@ int xrb_pack_bf16(const float *src, void *dst_bf16, int64_t n, void *stream) {
     int64_t blocks = (n / 4 + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16; if (blocks < 1) blocks = 1;
     pack_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16 *)dst_bf16, n);
     return check_launch("pack_bf16");
+}
+
+int xrb_tcnn_hashgrid_backward(const xrb_ngp_config *cfg, const float *x, int x_stride, int n, const void *d_enc_fp16, float grad_scale, float *d_table, void *stream) {
+    int e = check_cfg(cfg); if (e) return e;
+    XRB_REQUIRE(n >= 0 && x_stride >= 3, "hashgrid_backward: bad size");
+    if (n == 0) return XRB_OK;
+    XRB_REQUIRE(x && d_enc_fp16 && d_table, "hashgrid_backward: null pointer");
+    XRB_REQUIRE(((uintptr_t)d_table & 7) == 0 && ((uintptr_t)d_enc_fp16 & 3) == 0, "hashgrid_backward: misaligned");
+    HashGridDev g; hashgrid_build(cfg, &g);
+    int64_t threads = (int64_t)n * 16;
+    hashgrid_backward_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g, x, x_stride, n, (const __half2 *)d_enc_fp16, grad_scale, d_table);
+    return check_launch("hashgrid_backward");
+}
+
+int xrb_tcnn_mlp_backward(const void *params_fp16, const void *x_fp16, const void *dy_fp16, int n, int in_w, int width, int n_hidden, void *dx_fp16, float *d_params, void *stream) {
+    XRB_REQUIRE(n >= 0, "mlp_backward: negative size");
+    if (in_w != 32 || width != 64 || n_hidden < 1 || n_hidden > 4) { set_error("mlp_backward: only in=32 (padded), width=64, 1..4 hidden layers"); return XRB_E_UNSUPPORTED; }
+    if (n == 0) return XRB_OK;
+    XRB_REQUIRE(params_fp16 && x_fp16 && dy_fp16 && d_params, "mlp_backward: null pointer");
+    XRB_REQUIRE(((uintptr_t)x_fp16 & 15) == 0 && (!dx_fp16 || ((uintptr_t)dx_fp16 & 3) == 0), "mlp_backward: x must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (n_hidden) {
+        case 1: return launch_tcnn_mlp_bwd<1>(params_fp16, x_fp16, dy_fp16, n, dx_fp16, d_params, s);
+        case 2: return launch_tcnn_mlp_bwd<2>(params_fp16, x_fp16, dy_fp16, n, dx_fp16, d_params, s);
+        case 3: return launch_tcnn_mlp_bwd<3>(params_fp16, x_fp16, dy_fp16, n, dx_fp16, d_params, s);
+        default: return launch_tcnn_mlp_bwd<4>(params_fp16, x_fp16, dy_fp16, n, dx_fp16, d_params, s);
+    }
 }
 
 int xrb_ngp_mlp_backward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *density_fp16, const void *color_fp16, const float *pts, int pts_stride, const float *dirs,

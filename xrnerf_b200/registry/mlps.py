@@ -46,6 +46,18 @@ class NerfMLP(BaseMLP):
         del data['unflatten_shape']
         return data
 
+    # the packed tcgen05 weight image is keyed on Parameter._version, which writes through `.data` (EMAHook swap, load_state_dict, .to()) do not bump
+    def mark_dirty(self):
+        self._pack_ver = None
+
+    def _apply(self, fn, *a, **kw):
+        self._pack_ver = None
+        return super()._apply(fn, *a, **kw)
+
+    def _load_from_state_dict(self, *a, **kw):
+        self._pack_ver = None
+        return super()._load_from_state_dict(*a, **kw)
+
     def _fused_ok(self, x):
         return (self.fused and not torch.is_grad_enabled() and x.is_cuda and self.use_viewdirs and len(self.pts_linears) == 8 and list(self.skips) == [4]
                 and self.pts_linears[0].out_features == 256 and (self.input_ch, self.input_ch_dirs) in ((63, 27), (96, 27)))
@@ -122,6 +134,23 @@ class HashNerfMLP(BaseMLP):
         self.embedder_dir = _ParamHolder(nn.Parameter(torch.zeros(0)))
         self.density_net = _ParamHolder(f.density_params)
         self.color_net = _ParamHolder(f.color_params)
+
+    # the fused field caches fp16 shadows, the cell image and the UMMA weight image keyed on Parameter._version, which writes through `.data` (mmcv's EMAHook,
+    # load_state_dict's copy_, .to()) do not bump: every such entry point marks the caches dirty
+    def _apply(self, fn, *a, **kw):
+        self.field.mark_dirty()
+        return super()._apply(fn, *a, **kw)
+
+    def _load_from_state_dict(self, *a, **kw):
+        self.field.mark_dirty()
+        return super()._load_from_state_dict(*a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        self.field.mark_dirty()
+        return super().load_state_dict(*a, **kw)
+
+    def mark_dirty(self):
+        self.field.mark_dirty()
 
     def forward(self, data):
         shape = data['pts'].shape[:-1]

@@ -116,6 +116,9 @@ class NerfNetwork(nn.Module):
     def val_step(self, data, optimizer=None, **kwargs):
         """Renders data['poses'] through the installed val pipeline (rank 0 only in the reference; here every rank renders what it is given)."""
         data = {k: unfold_batching(v) for k, v in data.items()}
+        for m in (getattr(self, 'mlp', None), getattr(self, 'mlp_fine', None)):
+            if m is not None and hasattr(m, 'mark_dirty'):
+                m.mark_dirty()                      # weights may have been swapped through `.data` (EMAHook) since the last pack
         rgbs = []
         with torch.no_grad():
             for i in range(data['poses'].shape[0]):
@@ -195,6 +198,9 @@ class HashNerfNetwork(NerfNetwork):
         poses it is given. Returns the reference's keys plus 'psnr'."""
         if self.phase == 'test':
             return self.test_step(data, **kwargs)
+        # validation may run right after mmcv's EMAHook swapped the parameters through `.data` (Parameter._version unchanged): rebuild the fp16 shadows, the cell
+        # image and the UMMA weight image once per call instead of trusting the version key
+        self.mlp.mark_dirty()
         data = {k: unfold_batching(v) for k, v in data.items()}
         poses, images = data['poses'], data.get('images')
         rgbs, gt_imgs, psnrs, elapsed = [], [], [], []
@@ -222,6 +228,9 @@ class HashNerfNetwork(NerfNetwork):
         data = {k: unfold_batching(v) for k, v in data.items()}
         idx = data.get('idx', 0)
         idx = int(idx.item()) if torch.is_tensor(idx) else int(idx)
+        if idx == 0 or not getattr(self, '_test_refreshed', False):       # first pose of a test run: the weights may have been swapped / loaded through `.data`
+            self.mlp.mark_dirty()
+            self._test_refreshed = True
         with torch.no_grad():
             d = data if 'rays_o' in data else self.val_pipeline({'pose': data['poses'], 'idx': idx})
             ret = self.batchify_forward(d, is_test=True)

@@ -7,8 +7,11 @@
 so `import xrnerf_b200.tcnn as tcnn` lets the reference module run on the B200 kernels. Each module owns one flat fp32
 `params` nn.Parameter (tcnn's master-parameter layout: hash table levels back to back; MLP weight matrices W[out][in]
 row-major, first/hidden/last) and a cached fp16 working copy refreshed when `params` changes.
-The fused fast path (one kernel for encodings + both MLPs) lives in xrnerf_b200.ngp.NgpField; these modules are the
-composable, autograd-free* building blocks (*forward only in this round; training uses NgpField).
+Both modules are trainable like tcnn's: `params` receives gradients through torch.autograd (Encoding: table gradient by scatter; Network: input and
+parameter gradients), in the dtypes tcnn's bindings use (fp16 activations and activation gradients, fp32 parameter gradients), so the reference's
+`HashNerfMLP.run_mlp` (hashnerf_mlp.py:55-79) trains through them unchanged. The fused fast path (one kernel for encodings + both MLPs, tcgen05 forward and
+backward) lives in xrnerf_b200.ngp.NgpField; these modules are the composable building blocks behind the same parameter layouts:
+`export_params()` / `import_params()` move a flat tcnn parameter vector in and out (checkpoint compatibility).
 """
 import math
 
@@ -42,7 +45,66 @@ class _Fp16Shadow:
         return self.buf
 
 
-class Encoding(nn.Module):
+class _EncodingFn(torch.autograd.Function):
+    """HashGrid forward = xrb_tcnn_hashgrid_forward; backward scatters dL/d enc into the fp32 table gradient (positions are not differentiated: the
+    reference detaches them, hashnerf_mlp.py:58-59)."""
+
+    @staticmethod
+    def forward(ctx, mod, x, params):
+        ctx.mod = mod
+        ctx.save_for_backward(x)
+        return mod._forward(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        mod = ctx.mod
+        x, = ctx.saved_tensors
+        d = torch.zeros_like(mod.params, dtype=torch.float32)
+        g = g.contiguous().to(torch.float16)
+        xp, xs = _C.rows(x)
+        _C.check(_C.lib.xrb_tcnn_hashgrid_backward(mod.cfg, xp, xs, x.shape[0], _C.ptr(g), 1.0, _C.ptr(d), _C.stream()), 'hashgrid_backward')
+        return None, None, d
+
+
+class _NetworkFn(torch.autograd.Function):
+    """FullyFusedMLP forward = xrb_tcnn_mlp_forward; backward = xrb_tcnn_mlp_backward (recomputes the hidden activations; dX fp16, dW fp32)."""
+
+    @staticmethod
+    def forward(ctx, mod, x16, params):
+        ctx.mod = mod
+        ctx.save_for_backward(x16)
+        return mod._forward(x16)
+
+    @staticmethod
+    def backward(ctx, g):
+        mod = ctx.mod
+        x16, = ctx.saved_tensors
+        n = x16.shape[0]
+        g16 = torch.zeros((n, mod.out_pad), dtype=torch.float16, device=x16.device)
+        g16[:, :g.shape[1]] = g
+        d = torch.zeros_like(mod.params, dtype=torch.float32)
+        dx = torch.empty((n, mod.in_pad), dtype=torch.float16, device=x16.device) if ctx.needs_input_grad[1] else None
+        _C.check(_C.lib.xrb_tcnn_mlp_backward(_C.ptr(mod._shadow.get(mod.params)), _C.ptr(x16), _C.ptr(g16), n, mod.in_pad, mod.width, mod.n_hidden, _C.ptr(dx), _C.ptr(d),
+                                              _C.stream()), 'mlp_backward')
+        return None, dx, d
+
+
+class _ParamIO:
+    """flat-parameter import / export in tcnn's layout (`module.params` of the tcnn torch bindings; state_dict key `<name>.params`)"""
+
+    def export_params(self):
+        return self.params.detach().clone()
+
+    def import_params(self, flat):
+        flat = torch.as_tensor(flat)
+        if flat.numel() != self.params.numel():
+            raise ValueError(f'{type(self).__name__}: expected {self.params.numel()} parameters (tcnn layout), got {flat.numel()}')
+        with torch.no_grad():
+            self.params.copy_(flat.reshape(-1).to(self.params.dtype))
+        self._shadow.version = None                      # the fp16 working copy is rebuilt on the next forward
+
+
+class Encoding(nn.Module, _ParamIO):
     def __init__(self, n_input_dims, encoding_config, seed=1337):
         super().__init__()
         self.n_input_dims = int(n_input_dims)
@@ -74,6 +136,11 @@ class Encoding(nn.Module):
         x = x.detach().to(torch.float32)
         if x.stride(-1) != 1:
             x = x.contiguous()
+        if self.kind == 'hash' and torch.is_grad_enabled() and self.params.requires_grad:
+            return _EncodingFn.apply(self, x, self.params)
+        return self._forward(x)
+
+    def _forward(self, x):
         n = x.shape[0]
         out = torch.empty((n, self.n_output_dims), dtype=torch.float16, device=x.device)
         if self.kind == 'hash':
@@ -86,7 +153,7 @@ class Encoding(nn.Module):
         return out
 
 
-class Network(nn.Module):
+class Network(nn.Module, _ParamIO):
     def __init__(self, n_input_dims, n_output_dims, network_config, seed=1337):
         super().__init__()
         self.n_input_dims, self.n_output_dims = int(n_input_dims), int(n_output_dims)
@@ -111,11 +178,17 @@ class Network(nn.Module):
     def forward(self, x):
         _C.require_cuda(x)
         n = x.shape[0]
-        x = x.detach().to(torch.float16)
-        if x.shape[1] != self.in_pad:
+        x = x.to(torch.float16)
+        if x.shape[1] != self.in_pad:                    # tcnn.Network pads its input to a multiple of 16 with ones
             x = torch.cat([x, torch.ones((n, self.in_pad - x.shape[1]), dtype=torch.float16, device=x.device)], 1)
         x = x.contiguous()
+        if torch.is_grad_enabled() and (self.params.requires_grad or x.requires_grad):
+            return _NetworkFn.apply(self, x, self.params)[:, :self.n_output_dims]
+        return self._forward(x.detach())[:, :self.n_output_dims]
+
+    def _forward(self, x):
+        n = x.shape[0]
         y = torch.empty((n, self.out_pad), dtype=torch.float16, device=x.device)
         _C.check(_C.lib.xrb_tcnn_mlp_forward(_C.ptr(self._shadow.get(self.params)), _C.ptr(x), n, self.in_pad, self.width, self.n_hidden, _C.ptr(y), _C.stream()),
                  'mlp_forward')
-        return y[:, :self.n_output_dims]
+        return y
