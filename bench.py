@@ -25,6 +25,11 @@ import sys
 import threading
 import time
 
+if '--impl' in sys.argv and 'reference' in sys.argv or not os.environ.get('WORLD_SIZE'):
+    # the CPU legs use every host core; must happen before numpy / torch / the oracle load libgomp (see _omp_configure)
+    os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
+    os.environ.setdefault('OMP_PROC_BIND', 'close'); os.environ.setdefault('OMP_PLACES', 'cores'); os.environ.setdefault('OMP_DYNAMIC', 'false')
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -93,17 +98,42 @@ def make_scene(rank, n_batches=N_BATCHES):
 
 
 # ------------------------------------------------------------------------------------------- CPU arm (oracle; timing only)
-def cpu_reference_rate(sample_rays, reps=1):
-    """rays/s of the reference path on the host cores: reference march/composite kernels compiled for CPU (oracle/_ref, all
-    cores) + C restatement of the tcnn field (oracle port, OpenMP)."""
-    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (libgomp reads the variable when it is loaded)
+def _omp_configure():
+    """libgomp reads its environment when it is first loaded: pin and size the team BEFORE anything that links it (numpy/torch/the oracle .so) is imported.
+    torchrun exports OMP_NUM_THREADS=1, which round 1 overrode too late (VERDICT W8: 8.7 K ... 47 K rays/s for the same code)."""
     os.environ['OMP_NUM_THREADS'] = str(os.cpu_count() or 1)
+    os.environ.setdefault('OMP_PROC_BIND', 'close')
+    os.environ.setdefault('OMP_PLACES', 'cores')
+    os.environ.setdefault('OMP_DYNAMIC', 'false')
+
+
+def _omp_set_threads(k):
+    import ctypes
+    try:
+        ctypes.CDLL('libgomp.so.1').omp_set_num_threads(int(k))
+        return True
+    except Exception:
+        return False
+
+
+_CPU_SCENE = {}
+
+
+def cpu_reference_rate(sample_rays, reps=3, threads=None):
+    """rays/s of the reference path on the host cores: reference march/composite kernels compiled for CPU (oracle/_ref) + C restatement of the tcnn field
+    (oracle port), OpenMP with `threads` threads (default: all), best of `reps`."""
     from oracle import oracle as O
-    O.build()
-    port = O.Port()
-    use_ref = O.have_ref()
-    ref = O.Ref(serial=False) if use_ref else None
-    bf, batches, (table, dens, color) = make_scene(0, 1)
+    if 'port' not in _CPU_SCENE:
+        O.build()
+        _CPU_SCENE['port'] = O.Port()
+        _CPU_SCENE['ref'] = O.Ref(serial=False) if O.have_ref() else None
+        _CPU_SCENE['scene'] = make_scene(0, 1)
+    port, ref = _CPU_SCENE['port'], _CPU_SCENE['ref']
+    use_ref = ref is not None
+    bf, batches, (table, dens, color) = _CPU_SCENE['scene']
+    cores = os.cpu_count() or 1
+    threads = cores if threads is None else int(threads)
+    _omp_set_threads(threads)
     o, d = batches[0][0][:sample_rays], batches[0][1][:sample_rays]
     m = ref or port
     best = None
@@ -111,8 +141,6 @@ def cpu_reference_rate(sample_rays, reps=1):
     for _ in range(reps):
         t0 = time.perf_counter()
         c, _, ns, cnt = m.rays_sampler(o, d, bf, sample_rays * BUDGET)
-        if use_ref:  # parallel run: atomic-order layout, still (count, base) consistent
-            pass
         coords = c[:cnt[1]]
         raw = port.ngp_mlp_forward(table, dens, color, np.ascontiguousarray(coords[:, :3]), np.ascontiguousarray(coords[:, 4:]))
         rgb_cpu, alpha_cpu = m.calc_rgb_inference(raw, coords, ns, np.zeros(3, np.float32))
@@ -120,26 +148,38 @@ def cpu_reference_rate(sample_rays, reps=1):
         cpu_reference_rate.last = (np.asarray(rgb_cpu).copy(), np.asarray(alpha_cpu).copy(), np.asarray(ns)[:, 0].copy())
         best = dt if best is None else min(best, dt)
         n_samples = int(cnt[1])
-    cores = os.cpu_count() or 1
     kind = 'reference' if use_ref else 'port'
     sample = (f'{sample_rays} rays of batch 0 ({n_samples} samples): march+composite = reference ngp_raymarch kernels compiled for CPU '
-              f'(oracle/_ref, OpenMP), field = C restatement of tcnn (oracle port, OpenMP); best of {reps}') if use_ref else \
-             f'{sample_rays} rays of batch 0 ({n_samples} samples), plain-C oracle port, OpenMP; best of {reps}'
-    return sample_rays / best, cores, kind, sample, best
+              f'(oracle/_ref, OpenMP), field = C restatement of tcnn (oracle port, OpenMP); {threads} threads (OMP_PROC_BIND=close, OMP_PLACES=cores), best of {reps}') if use_ref else \
+             f'{sample_rays} rays of batch 0 ({n_samples} samples), plain-C oracle port, OpenMP, {threads} threads; best of {reps}'
+    return sample_rays / best, threads, kind, sample, best
+
+
+def cpu_thread_sweep(sample_rays, reps=3):
+    """thread counts {1, 16, 64, all}: the fastest setting is the baseline, every setting is reported"""
+    cores = os.cpu_count() or 1
+    sweep = {}
+    for k in sorted({1, min(16, cores), min(64, cores), cores}):
+        r, _, kind, sample, best = cpu_reference_rate(sample_rays, reps=reps, threads=k)
+        sweep[k] = (r, kind, sample, best)
+    k_best = max(sweep, key=lambda k: sweep[k][0])
+    r, kind, sample, best = sweep[k_best]
+    return r, k_best, kind, sample + f'; thread sweep rays/s: ' + ', '.join(f'{k}: {v[0]:.0f}' for k, v in sweep.items()), best
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    rates = []
     t_start = time.time()
     sample_rays = 8192
-    for _ in range(args.warmup):
-        cpu_reference_rate(1024)
-    per = []
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_rate(1024, reps=1)
+    # thread sweep once (which team size is fastest on this box), then the timed steps at that setting
+    _, k_best, kind, _, _ = cpu_thread_sweep(2048, reps=2)
+    rates, per = [], []
     for _ in range(args.steps):
-        r, cores, kind, sample, dt = cpu_reference_rate(sample_rays)
+        r, cores, kind, sample, dt = cpu_reference_rate(sample_rays, reps=1, threads=k_best)
         rates.append(r); per.append(dt)
         if time.time() - t_start > 240:
             break
@@ -147,11 +187,33 @@ def run_reference(args):
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': args.gpus, 'steps': len(rates), 'warmup': args.warmup,
         'ms_per_step': float(np.median(per) * 1e3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'note': f'each step = a bounded sample of {sample_rays} rays of the 65536-ray batch on the host cores'},
-        'cpu_baseline': {'value': value, 'unit': 'rays/s', 'cores': cores, 'kind': kind, 'sample': sample},
+        'config': {'workload': WORKLOAD, 'note': f'each step = a bounded sample of {sample_rays} rays of the 65536-ray batch on the host cores; median over the steps; '
+                                                 f'spread min {min(rates):.0f} / max {max(rates):.0f} rays/s'},
+        'cpu_baseline': {'value': value, 'unit': 'rays/s', 'cores': cores, 'kind': kind, 'sample': sample + f'; team size chosen by a sweep over 1/16/64/all threads'},
         'e2e': {'value': value, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def nerf_convention_rays(dev, n, seed, with_radii=False):
+    """BASELINE-convention rays for the NeRF / Mip-NeRF arms (VERDICT W9): Blender spiral pose (pose_spherical(theta, -30, 4.0), load_blender.py:22-29,72-75), 800x800 f=1111.1 camera,
+    GetRays + GetViewdirs conventions (create.py:205-245,:437-448) through xrb_nerf_get_rays on `n` random pixels; near 2 / far 6 (load.py:58-59)."""
+    import torch
+    from xrnerf_b200 import _C, synth
+    rng = np.random.default_rng(seed)
+    pose = synth.pose_spherical(float(rng.uniform(-180, 180)), -30.0, 4.0)
+    pix = torch.from_numpy(rng.integers(0, 800 * 800, n).astype(np.int32)).to(dev)
+    c2w = (_C.C.c_float * 12)(*[float(v) for v in pose[:3, :4].reshape(-1)])
+    o = torch.empty((n, 3), device=dev); d = torch.empty((n, 3), device=dev); v = torch.empty((n, 3), device=dev)
+    r = torch.empty((n, 1), device=dev) if with_radii else None
+    _C.check(_C.lib.xrb_nerf_get_rays(c2w, 800, 800, float(synth.FOCAL), float(synth.FOCAL), 400.0, 400.0, 0, _C.ptr(pix), n, _C.ptr(o), _C.ptr(d), _C.ptr(v), _C.ptr(r), _C.stream()), 'get_rays')
+    return (o, d, v, r) if with_radii else (o, d, v)
+
+
+def psnr_obj(a, b, what):
+    err = np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))
+    mse = float((err ** 2).mean())
+    return {'rays': int(a.shape[0]), 'max_abs_rgb_err': float(err.max()), 'psnr_vs_ref_db': float(-10.0 * np.log10(max(mse, 1e-20))), 'against': what}
 
 
 # ------------------------------------------------------------------------------------------- our arm
@@ -233,6 +295,53 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     clk = clocks.stop() if rank == 0 else None
+
+    # ---- isolated pass (P = 1, one stream): the dominant kernel timed ALONE, so that kernel_ms <= the step it is part of (round 1 recorded the events while three other
+    # streams shared the SMs: kernel_share_of_step 1.06 > 1). Distinct batches every step (inputs > L2); event pair around the field kernel inside xrb_ngp_render and
+    # around the whole 5-launch call.
+    KI_ = min(K, 24)
+    ev_f = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KI_)]
+    ev_c = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KI_)]
+    iso_cnt = []
+    for i in range(3):
+        renderers[0].render(*dev_batches[(i + 40) % N_BATCHES], bf)
+    barrier()
+    for i in range(KI_):
+        for e in ev_f[i]:
+            e.record(main)
+        ev_c[i][0].record(main)
+        out = renderers[0].render(*dev_batches[(i + 48) % N_BATCHES], bf, profile_events=ev_f[i])
+        ev_c[i][1].record(main)
+        iso_cnt.append(out[3].clone())
+    barrier()
+    iso_field_ms = float(np.median([a.elapsed_time(b) for a, b in ev_f]))
+    iso_chain_ms = float(np.median([a.elapsed_time(b) for a, b in ev_c]))
+    iso_samples = float(np.mean([int(c[1].item()) for c in iso_cnt]))
+
+    # ---- the roof the gather actually runs under: random 4-byte reads from an L2-resident table of the hash table's size (xrb_micro_gather). Every read costs one 32-byte
+    # sector; the rate is reported as sectors x 32 B / s next to the HBM copy peak the contract's roofline is quoted against.
+    l2_roof = None
+    try:
+        tbl = torch.empty(24_400_000 // 4, dtype=torch.int32, device=dev).random_()
+        sink = torch.zeros(4, dtype=torch.int32, device=dev)
+        n_loads = _C.C.c_int64(0)
+        res_roof = {}
+        for wbytes in (4, 32):
+            nrec = tbl.numel() * 4 // wbytes
+            for _ in range(2):
+                _C.check(_C.lib.xrb_micro_gather(_C.ptr(tbl), nrec, wbytes, 64, _C.C.byref(n_loads), _C.ptr(sink), _C.stream()), 'micro_gather')
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(main)
+            for _ in range(5):
+                _C.check(_C.lib.xrb_micro_gather(_C.ptr(tbl), nrec, wbytes, 64, _C.C.byref(n_loads), _C.ptr(sink), _C.stream()), 'micro_gather')
+            r1.record(main)
+            torch.cuda.synchronize()
+            res_roof[wbytes] = 5 * n_loads.value / (r0.elapsed_time(r1) * 1e-3)
+        l2_roof = {'random_4B_loads_per_s': res_roof[4], 'random_32B_loads_per_s': res_roof[32], 'sector_GBs_at_4B': res_roof[4] * 32 / 1e9, 'sector_GBs_at_32B': res_roof[32] * 32 / 1e9,
+                   'what': 'xrb_micro_gather: random reads from a 24.4 MB (L2-resident) table, 8 independent loads in flight per thread, SMs x 8 CTAs x 256 threads; one 32-byte sector per load'}
+        del tbl
+    except Exception as e:
+        l2_roof = {'error': repr(e)[:200]}
 
     # ---- single-launch arm: the same K steps through xrb_ngp_render_fused (march + encode + tcgen05 MLPs + composite in ONE kernel per batch)
     evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -454,6 +563,35 @@ def run_ours(args):
         except Exception as e:   # an auxiliary arm must never take the headline line down
             grid_upd = {'error': repr(e)[:300]}
 
+    # ---- all-ones occupancy grid (the first 256 training iterations, ngp_grid_sampler.py:168-174): every cell occupied, rays carry hundreds of samples
+    all_ones = None
+    if not args.no_image:
+        try:
+            n_ao = 8192
+            bf_ones = torch.full_like(bf, 255)
+            ao_r = NgpRenderer(field, samples_per_ray_budget=1024)
+            res_ao = {}
+            for path in ('chain', 'fused'):
+                fn = (lambda o_, d_: ao_r.render_fused(o_, d_, bf_ones)) if path == 'fused' else (lambda o_, d_: ao_r.render(o_, d_, bf_ones))
+                for i in range(2):
+                    fn(dev_batches[i][0][:n_ao], dev_batches[i][1][:n_ao])
+                barrier()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                KA = 6
+                a0.record()
+                for i in range(KA):
+                    out_a = fn(dev_batches[(i + 2) % N_BATCHES][0][:n_ao], dev_batches[(i + 2) % N_BATCHES][1][:n_ao])
+                a1.record()
+                barrier()
+                ns_a = out_a[2]
+                spr_a = float((ns_a[:, 0] if ns_a.dim() == 2 else ns_a).float().mean().item())
+                ms_a = a0.elapsed_time(a1) / KA
+                res_ao[path] = {'value': world * n_ao / (ms_a * 1e-3), 'unit': 'rays/s', 'ms_per_batch': ms_a, 'samples_per_ray_mean': spr_a, 'samples_per_s': world * n_ao * spr_a / (ms_a * 1e-3)}
+            all_ones = dict(res_ao, what=f'all-ones bitfield, {n_ao}-ray batches (sample budget 1024 per ray on the chain path), sequential calls on one stream')
+            del ao_r
+        except Exception as e:
+            all_ones = {'error': repr(e)[:300]}
+
     # ---- NeRF arm (BASELINE configs[2]: hierarchical 64 + 128, 800x800-shaped rays): fused tcgen05 NerfMLP path, device-resident rays
     nerf = None
     if not args.no_nerf:
@@ -465,16 +603,15 @@ def run_ours(args):
                                        render=dict(type='NerfRender', white_bkgd=True, raw_noise_std=0))).to(dev)
             nr = NerfRenderer(net, near=2.0, far=6.0, n_samples=64)
             n_nerf = 32768
-            ro, rd = dev_batches[0][0][:n_nerf].contiguous(), dev_batches[0][1][:n_nerf].contiguous()
+            nerf_rays = [nerf_convention_rays(dev, n_nerf, 500 + 10 * rank + b) for b in range(8)]
             for _ in range(3):
-                nr.render(ro, rd, rd)
+                nr.render(*nerf_rays[0])
             barrier()
             n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             KN = max(3, min(K, 20))
             n0.record()
             for i in range(KN):
-                o_i = dev_batches[i % N_BATCHES][0][:n_nerf]; d_i = dev_batches[i % N_BATCHES][1][:n_nerf]
-                nr.render(o_i, d_i, d_i)
+                nr.render(*nerf_rays[i % 8])
             n1.record()
             barrier()
             nm = torch.tensor([n0.elapsed_time(n1)], dtype=torch.float64, device=dev)
@@ -490,11 +627,22 @@ def run_ours(args):
             # CPU baseline leg of this arm (rank 0, N=1): BASELINE configs[0] shape - 1024 rays x 64 samples, coarse network only - through the numpy oracle
             # (embed -> 12-layer NerfMLP -> composite; multi-threaded BLAS on the box's host cores). Checker code, timed only.
             nerf_cpu = None
+            nerf_parity = None
             if world == 1:
                 try:
                     from oracle import nerf_oracle as NO
                     sd = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
-                    o_c = dev_batches[0][0][:1024].cpu().numpy(); d_c = dev_batches[0][1][:1024].cpu().numpy()
+                    # parity of THIS arm on its own rays: 512 of the timed rays through the numpy restatement of the reference's hierarchical forward (fp32) vs the fused tcgen05 path (fp16 operands)
+                    po, pd, pv = (t[:512].contiguous() for t in nerf_rays[0])
+                    got = nr.render(po, pd, pv)
+                    o_p, d_p, v_p = po.cpu().numpy(), pd.cpu().numpy(), pv.cpu().numpy()
+                    z_p = np.broadcast_to(np.linspace(2, 6, 64, dtype=np.float32), (512, 64)).copy()
+                    pts_p = o_p[:, None] + d_p[:, None] * z_p[..., None]
+                    c_p = NO.nerf_render(NO.nerf_mlp(sd, NO.embed(pts_p, v_p), 63, 27, prefix='mlp.').reshape(512, 64, 4), z_p, d_p, white_bkgd=True)
+                    z2_p, pts2_p, _ = NO.sample_pdf(z_p, c_p['weights'], o_p, d_p, 128)
+                    f_p = NO.nerf_render(NO.nerf_mlp(sd, NO.embed(pts2_p, v_p), 63, 27, prefix='mlp_fine.').reshape(512, 192, 4), z2_p, d_p, white_bkgd=True)
+                    nerf_parity = psnr_obj(got['rgb'].cpu().numpy(), f_p['rgb'], 'oracle/nerf_oracle.py (numpy fp32 restatement of NerfNetwork.forward, pinned to the reference by tests/golden)')
+                    o_c = o_p.repeat(2, 0); d_c = d_p.repeat(2, 0)
                     z_c = np.broadcast_to(np.linspace(2, 6, 64, dtype=np.float32), (1024, 64)).copy()
                     best = None
                     for _ in range(2):
@@ -508,7 +656,7 @@ def run_ours(args):
                                 'sample': 'configs[0]: 1024 rays x 64 samples, coarse network only, numpy oracle (fp32, multi-threaded BLAS); best of 2'}
                 except Exception as e:
                     nerf_cpu = {'error': repr(e)[:200]}
-            nerf = {'value': rps, 'unit': 'rays/s', 'cpu_baseline': nerf_cpu, 'workload': 'vanilla NeRF hierarchical 64 coarse + 192 fine evaluations per ray (configs[2]), 32768-ray batches, inference',
+            nerf = {'value': rps, 'unit': 'rays/s', 'cpu_baseline': nerf_cpu, 'parity': nerf_parity, 'rays': 'NeRF convention (GetRays on random pixels of Blender spiral poses, radius 4), near 2 / far 6', 'workload': 'vanilla NeRF hierarchical 64 coarse + 192 fine evaluations per ray (configs[2]), 32768-ray batches, inference',
                     'ms_per_batch': float(nm.item()) / KN, 'roofline': {'bound': 'tensor', 'achieved': rps * flop_per_ray / 1e12 / world, 'peak': tpeak, 'unit': 'TFLOP/s',
                                                                          'frac': rps * flop_per_ray / 1e12 / world / tpeak, 'flop_per_ray': flop_per_ray,
                                                                          'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a multi-kernel step)'}}
@@ -567,16 +715,15 @@ def run_ours(args):
                                         render=dict(type='MipNerfRender', white_bkgd=True, raw_noise_std=0, rgb_padding=0.001, density_bias=-1, density_activation='softplus'))).to(dev)
             mr = MipNerfRenderer(mnet, near=2.0, far=6.0, n_samples=128)
             n_mip = 32768
-            radii = torch.full((n_mip,), 2.0 / (1111.111 * 12 ** 0.5), device=dev)        # GetRays radii of an 800x800 f=1111 camera: |dx| * 2/sqrt(12) (create.py:237-243)
+            mip_rays = [nerf_convention_rays(dev, n_mip, 700 + 10 * rank + b, with_radii=True) for b in range(8)]   # radii = |dx| * 2/sqrt(12) from GetRays (create.py:237-243)
             for i in range(3):
-                mr.render(dev_batches[0][0][:n_mip], dev_batches[0][1][:n_mip], dev_batches[0][1][:n_mip], radii)
+                mr.render(*mip_rays[0])
             barrier()
             m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             KM = max(3, min(K, 20))
             m0.record()
             for i in range(KM):
-                o_i = dev_batches[i % N_BATCHES][0][:n_mip]; d_i = dev_batches[i % N_BATCHES][1][:n_mip]
-                mr.render(o_i, d_i, d_i, radii)
+                mr.render(*mip_rays[i % 8])
             m1.record()
             barrier()
             mm = torch.tensor([m0.elapsed_time(m1)], dtype=torch.float64, device=dev)
@@ -589,7 +736,28 @@ def run_ours(args):
                     tpeak = float(json.load(fh)['bf16_tflops_sustained'])
             except Exception:
                 tpeak = 1400.0
-            mip = {'value': mrps, 'unit': 'rays/s', 'workload': 'Mip-NeRF 2 levels x 128 conical-frustum samples per ray, IPE 96 + 27 (configs[3]), 32768-ray batches, inference',
+            mip_parity = None
+            if world == 1:
+                try:
+                    from oracle import nerf_oracle as NO
+                    sdm = {k: v.detach().cpu().numpy() for k, v in mnet.state_dict().items()}
+                    po, pd, pv, pr = (t[:256].contiguous() for t in mip_rays[0])
+                    got = mr.render(po, pd, pv, pr)
+                    o_p, d_p, v_p, r_p = po.cpu().numpy(), pd.cpu().numpy(), pv.cpu().numpy(), pr.cpu().numpy()
+                    z_p = np.broadcast_to(np.linspace(2, 6, 129, dtype=np.float32), (256, 129)).copy()
+                    rgb_levels = []
+                    for level in range(2):
+                        if level > 0:
+                            z_p = NO.resample_along_rays(z_p, w_p, 0.01)
+                        means, covs = NO.cast_rays(z_p, o_p, d_p, r_p)
+                        emb = np.concatenate([NO.integrated_pos_enc(means, covs, 0, 16).reshape(256 * 128, -1), np.repeat(NO.mip_pos_enc(v_p, 0, 4), 128, 0)], -1)
+                        raw_p = NO.nerf_mlp(sdm, emb, 96, 27, prefix='mlp.').reshape(256, 128, 4)
+                        rl = NO.nerf_render(raw_p, z_p, d_p, white_bkgd=True, rgb_padding=0.001, density_bias=-1.0, density_activation='softplus', mip=True)
+                        w_p = rl['weights']; rgb_levels.append(rl['rgb'])
+                    mip_parity = psnr_obj(got['rgb'].cpu().numpy(), rgb_levels[-1], 'oracle/nerf_oracle.py (numpy fp32 restatement of MipNerfNetwork.forward, pinned to the reference by tests/golden)')
+                except Exception as e:
+                    mip_parity = {'error': repr(e)[:300]}
+            mip = {'value': mrps, 'unit': 'rays/s', 'parity': mip_parity, 'rays': 'NeRF convention with GetRays radii, near 2 / far 6', 'workload': 'Mip-NeRF 2 levels x 128 conical-frustum samples per ray, IPE 96 + 27 (configs[3]), 32768-ray batches, inference',
                    'ms_per_batch': float(mm.item()) / KM, 'roofline': {'bound': 'tensor', 'achieved': mrps * mflop / 1e12 / world, 'peak': tpeak, 'unit': 'TFLOP/s',
                                                                        'frac': mrps * mflop / 1e12 / world / tpeak, 'flop_per_ray': mflop,
                                                                        'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a multi-kernel step)'}}
@@ -598,10 +766,14 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        f_ms = float(np.mean(field_ms))
+        f_ms_loaded = float(np.mean(field_ms))                      # the same kernel's events recorded while P-1 other batches shared the SMs (context only)
         s_mean = float(np.mean(samples))
-        achieved = s_mean * BYTES_PER_SAMPLE / (f_ms * 1e-3) / 1e9
-        cpu_rate, cores, kind, sample, _ = cpu_reference_rate(4096, reps=2) if world == 1 else (None, os.cpu_count(), 'reference', 'measured at N=1 only', None)
+        achieved = iso_samples * BYTES_PER_SAMPLE / (iso_field_ms * 1e-3) / 1e9
+        if world == 1:
+            cpu_rate, cores, kind, sample, _ = cpu_thread_sweep(4096, reps=3)
+            cpu_reference_rate(4096, reps=1, threads=cores)          # leaves the 4096-ray render in cpu_reference_rate.last for the parity object
+        else:
+            cpu_rate, cores, kind, sample = None, os.cpu_count(), 'reference', 'measured at N=1 only'
         parity = None
         if world == 1:   # the CPU arm just rendered 4096 rays of batch 0 with the reference arithmetic: compare this arm's render of the same rays (checker only)
             rgb_cpu, alpha_cpu, ns_cpu = cpu_reference_rate.last
@@ -610,42 +782,57 @@ def run_ours(args):
                 err = np.abs(rgb_g - rgb_cpu)
                 mse = float((err.astype(np.float64) ** 2).mean())
                 parity[path] = {'max_abs_rgb_err': float(err.max()), 'psnr_vs_ref_db': float(-10.0 * np.log10(max(mse, 1e-20))), 'sample_counts_bit_exact': bool(np.array_equal(ns_g, ns_cpu))}
-        chain = {'value': world * N_RAYS * K / (total_ms_max * 1e-3), 'unit': 'rays/s', 'ms_per_step': total_ms_max / K, 'gpu_launches_per_step': 5,
-                 'what': '5 launches per batch on one stream (march count / scan / emit, field, composite), P batches in flight on P streams',
+        # L2 -> SM sector traffic of ONE field launch at this workload, from the committed ncu --set full capture (profiles/r02_ngp_field_tc_ncu.md: lts__t_sectors_srcunit_tex_op_read.sum
+        # = 30.29 M sectors for 699 K samples = 43.3 sectors per sample): scaled to this run's sample count. DRAM traffic of the same capture: 47.15 MB read + 4.88 MB written.
+        SECTORS_PER_SAMPLE = 30292243 / 699130
+        l2_bytes = iso_samples * SECTORS_PER_SAMPLE * 32
+        l2_obj = None
+        if l2_roof and 'error' not in l2_roof:
+            l2_obj = {'bound': 'l2 sector rate (random 4-byte gather)', 'achieved': l2_bytes / (iso_field_ms * 1e-3) / 1e9, 'peak': l2_roof['sector_GBs_at_4B'], 'unit': 'GB/s of 32-byte sectors',
+                      'frac': l2_bytes / (iso_field_ms * 1e-3) / 1e9 / l2_roof['sector_GBs_at_4B'], 'sectors_per_sample': SECTORS_PER_SAMPLE,
+                      'sectors_source': 'quoted: ncu capture profiles/r02_ngp_field_tc_ncu.md (lts__t_sectors_srcunit_tex_op_read.sum / samples), scaled to this run', 'peak_measured_live': l2_roof}
+        chain = {'value': world * N_RAYS * K / (total_ms_max * 1e-3), 'unit': 'rays/s', 'ms_per_step': total_ms_max / K, 'gpu_launches_per_step': 6,
+                 'what': '6 launches per batch on one stream (memset, march count / scan / emit, field, composite), P batches in flight on P streams',
                  'roofline': {'kernel': 'xrb::ngp_field_tc_kernel<false>', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                              'kernel_ms': f_ms, 'kernel_share_of_step': f_ms / (total_ms_max / K), 'algorithmic_bytes_per_launch': s_mean * BYTES_PER_SAMPLE}}
+                              'kernel_ms': iso_field_ms, 'kernel_share_of_step': iso_field_ms / iso_chain_ms, 'step_ms_sequential': iso_chain_ms,
+                              'timing': 'isolated pass: one stream, one batch at a time, CUDA events around the kernel inside xrb_ngp_render and around the whole call, median of %d' % KI_,
+                              'kernel_ms_with_other_batches_in_flight': f_ms_loaded, 'algorithmic_bytes_per_launch': iso_samples * BYTES_PER_SAMPLE, 'l2_gather_roofline': l2_obj}}
         f_bytes = fused_samples * 512 + N_RAYS * 44   # no coords[S,7] / raw[S,4] round trip: gather bytes + 44 B of ray I/O
         f_ach = f_bytes / (fused_kernel_ms * 1e-3) / 1e9
         fused = {'value': world * N_RAYS * K / (fused_total_ms * 1e-3), 'unit': 'rays/s', 'ms_per_step': fused_total_ms / K, 'gpu_launches_per_step': 1,
                  'what': 'ONE launch per batch (xrb_ngp_render_fused: warp-specialised march + hash encode + tcgen05 MLPs + segmented-scan composite), P batches in flight on P streams',
                  'roofline': {'kernel': 'xrb::ngp_render_fused_kernel', 'bound': 'hbm', 'achieved': f_ach, 'peak': peak, 'unit': 'GB/s', 'frac': f_ach / peak,
-                              'kernel_ms': fused_kernel_ms, 'kernel_share_of_step': 1.0, 'algorithmic_bytes_per_launch': f_bytes}}
+                              'kernel_ms': fused_kernel_ms, 'kernel_share_of_step': 1.0, 'kernel_ms_note': 'events around the launch while P-1 other launches share the SMs',
+                              'algorithmic_bytes_per_launch': f_bytes}}
         head = fused if use_fused else chain
         line = {
             'metric': METRIC, 'value': head['value'], 'unit': 'rays/s', 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': head['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'rays_per_step_per_gpu': N_RAYS, 'samples_per_ray_mean': s_mean / N_RAYS, 'parallelism': f'ray-sharded x{world}, no data-path collective',
-                       'l2': f'inputs larger than L2: {N_BATCHES} distinct ray batches = {N_BATCHES * N_RAYS * 24 / 1e6:.0f} MB cycled (L2 126 MB); the 24.4 MB fp16 hash table stays L2-resident as in production',
+                       'l2': f'inputs larger than L2: {N_BATCHES} distinct ray batches = {N_BATCHES * N_RAYS * 24 / 1e6:.0f} MB cycled (L2 126 MB), nothing flushed; the 24.4 MB fp16 hash table and its '
+                             f'{field._cells.numel() / 1e6 if field._cells is not None else 0:.0f} MB cell image (levels 0..{field.n_packed - 1}) stay L2-resident as in production',
                        'timing': 'one CUDA-event pair around the K steps on the launching stream, max over ranks', 'batches_in_flight': P, 'untimed_warmup_steps_run': WU,
-                       'path': 'fused single launch' if use_fused else 'chain of 5 launches', 'path_selection': args.path},
+                       'path': 'fused single launch' if use_fused else 'chain of 6 launches', 'path_selection': args.path, 'cell_image_levels': field.n_packed},
             'clocks': clk,
             'e2e': {'value': world * N_RAYS * K / (e2e_ms * 1e-3), 'unit': 'rays/s', 'h2d_bytes_per_step': N_RAYS * 24, 'd2h_bytes_per_step': N_RAYS * 16,
                     'ms_per_step': e2e_ms / K, 'host_wall_ms_per_step': e2e_wall_ms / K},
             'gpu_launches': head['gpu_launches_per_step'] * K,
-            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of that kernel at this workload, from the committed ncu --set full captures
-            # (profiles/r01b_ngp_field_tc_ncu.md: 41.88 MB + 1.64 MB; profiles/r01b_ngp_render_fused_ncu.md: 27.80 MB + 0.04 MB) - far below the algorithmic
-            # bytes because the gather is served by L2/L1
-            'roofline': dict(head['roofline'], traffic=(27.80e6 + 0.04e6) if use_fused else (41.88e6 + 1.64e6), traffic_source='ncu --set full capture committed under profiles/ (r01b), bytes per launch', peak_source=peak_src,
-                             note='hash table (24.4 MB fp16) is L2-resident by design: the gather is served by L1/L2, so DRAM traffic (ncu, profiles/) is far below the algorithmic bytes'),
+            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at this workload, QUOTED from the committed ncu --set full capture of this
+            # round (profiles/r02_ngp_field_tc_ncu.md: 47.15 MB + 4.88 MB; fused kernel: profiles/r01b_ngp_render_fused_ncu.md 27.80 MB + 0.04 MB), not measured by this run
+            'roofline': dict(head['roofline'], traffic=(27.80e6 + 0.04e6) if use_fused else (47.15e6 + 4.88e6), traffic_source='quoted from the ncu --set full capture committed under profiles/ (bytes per launch); not measured by this run',
+                             peak_source=peak_src,
+                             note='hash table (24.4 MB fp16) + cell image are L2-resident by design: DRAM traffic is far below the algorithmic bytes; the gather runs under the L2 sector rate '
+                                  '(l2_gather_roofline: every 4-byte entry costs a 32-byte sector), not under the HBM copy peak this frac is quoted against'),
             'paths': {'chain': chain, 'fused': fused},
             'cpu_baseline': {'value': cpu_rate, 'unit': 'rays/s', 'cores': cores, 'kind': kind, 'sample': sample},
             'parity': parity,
             'image': image_arm,
-            'train': train,
             'grid_update': grid_upd,
             'nerf': nerf,
             'nerf_train': nerf_train,
             'mip': mip,
+            'all_ones_grid': all_ones,
+            'train': train,                                   # last on purpose: the driver keeps the tail of the line
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -309,8 +309,21 @@ int xrb_mip_resample(const float *z_vals, const float *weights, const float *u, 
  * camera-to-world. pixel_idx i32[n] (row-major pixel numbers) or NULL for the first n pixels. viewdirs / radii may be NULL. */
 int xrb_nerf_get_rays(const float *c2w_host, int H, int W, float fx, float fy, float cx, float cy, int convention, const int32_t *pixel_idx, int64_t n, float *rays_o, float *rays_d,
                       float *viewdirs, float *radii, void *stream);
+/* The NGP training-ray source on the device: replaces the 2.8 GB shuffled host table of HashNerfDataset (datasets/load_data/get_rays.py:72-98,
+ * hashnerf_dataset.py:41-44) + HashBatchSample (datasets/pipelines/create.py:153-190) + RandomBGColor (datasets/pipelines/augment.py:290-313).
+ * poses f32[I,4,3] (NGP xforms), images_rgba f32[I,H,W,4]; row_idx i64[n] = rows of the (virtual) [I*H*W, 11] table, i.e. a slice of the caller's permutation;
+ * u_bg f32[n,3] = the background uniforms, or NULL to draw them on the device from (seed, n_prior_calls). Outputs as the reference's data dict:
+ * rays_o, rays_d f32[n,3] (unit dirs), target_s f32[n,3] (blended with the background), alpha f32[n,1], img_ids f32[n,1], bg_color f32[n,3]. */
+int xrb_ngp_batch_sample(const float *poses, const float *images_rgba, int n_images, int H, int W, float fx, float fy, float cx, float cy, const int64_t *row_idx, int64_t n,
+                         const float *u_bg, uint64_t seed, int64_t n_prior_calls, float *rays_o, float *rays_d, float *target_s, float *alpha, float *img_ids, float *bg_color,
+                         void *stream);
 /* GetZvals (create.py:502-531, near/far constants) and, with u f32[n_rays, S] != NULL, PerturbZvals (augment.py:269-283) */
 int xrb_nerf_zvals(int64_t n_rays, int n_samples, float near_, float far_, int lindisp, const float *u, float *z_vals, void *stream);
+
+/* Measurement utility (bench.py's second roofline; no reference counterpart): random reads of 4-, 8- or 32-byte records from a table (L2-resident when
+ * it is the size of the fp16 hash table) by SMs x 8 CTAs x 256 threads, `rounds` rounds of 8 independent loads per thread. *loads_issued (host) receives the
+ * number of loads of the launch; every 4/8-byte load costs one 32-byte sector, which is what bounds the hash gather. */
+int xrb_micro_gather(const void *table, int64_t n_records, int record_bytes, int rounds, int64_t *loads_issued, void *sink, void *stream);
 
 #ifdef __cplusplus
 }

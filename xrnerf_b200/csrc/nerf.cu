@@ -491,6 +491,42 @@ __device__ __forceinline__ void raygen_dir(const RayGenParams &p, float i, float
 #pragma unroll
     for (int c = 0; c < 3; ++c) d[c] = (x * p.c2w[4 * c] + y * p.c2w[4 * c + 1]) + z * p.c2w[4 * c + 2];
 }
+// The NGP training-ray source on the device: what HashNerfDataset + HashBatchSample + RandomBGColor produce on the host
+//   load_rays_hash (datasets/load_data/get_rays.py:72-98): row r of the [I*H*W, 11] table = (rays_o3, rays_d3 by get_rays_np_hash, rgba4, image id) of pixel r % (H*W) of image r / (H*W)
+//   the table shuffle (hashnerf_dataset.py:41-44) = the caller's row permutation; HashBatchSample (create.py:153-190) = a slice of it
+//   RandomBGColor (augment.py:290-313): bg = U[0,1)^3, target = rgb * alpha + bg * (1 - alpha) (float64 on the host, rounded to fp32)
+// without the 2.8 GB host table: one thread per ray regenerates its row from (pose, pixel) and blends the background.
+__global__ void __launch_bounds__(256) ngp_batch_sample_kernel(const float *__restrict__ poses, const float *__restrict__ images, int n_img, int H, int W, float fx, float fy, float cx,
+                                                               float cy, const int64_t *__restrict__ row_idx, int64_t n, const float *__restrict__ u_bg, Pcg32 rng,
+                                                               float *__restrict__ rays_o, float *__restrict__ rays_d, float *__restrict__ target_s, float *__restrict__ alpha_out,
+                                                               float *__restrict__ img_ids, float *__restrict__ bg_color) {
+    const int64_t hw = (int64_t)H * W;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = row_idx[t];
+        const int img = (int)(row / hw), pix = (int)(row % hw), j = pix / W, i = pix % W;
+        const float *P = poses + (size_t)img * 12;                 // [4,3]: rows 0..2 = rotation columns (c2w = P^T), row 3 = camera origin
+        const float x = ((float)i + 0.5f - cx) / fx, y = ((float)j + 0.5f - cy) / fy;
+        float d[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d[c] = (x * P[c] + y * P[3 + c]) + P[6 + c];
+        const float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        const float4 px = *reinterpret_cast<const float4 *>(images + ((size_t)img * hw + pix) * 4);
+        float u[3];
+        if (u_bg) { u[0] = u_bg[3 * t]; u[1] = u_bg[3 * t + 1]; u[2] = u_bg[3 * t + 2]; }
+        else { Pcg32 r = rng; r.advance((uint64_t)t * 3u); u[0] = r.next_float(); u[1] = r.next_float(); u[2] = r.next_float(); }
+        const float rgb[3] = {px.x, px.y, px.z};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            rays_o[3 * t + c] = P[9 + c];
+            rays_d[3 * t + c] = d[c] / nrm;
+            target_s[3 * t + c] = (float)((double)(rgb[c] * px.w) + (double)u[c] * (double)(1.f - px.w));
+            bg_color[3 * t + c] = u[c];
+        }
+        alpha_out[t] = px.w;
+        img_ids[t] = (float)img;
+    }
+}
+
 __global__ void __launch_bounds__(256) get_rays_kernel(RayGenParams p, const int32_t *__restrict__ pixel_idx, int64_t n, float *__restrict__ rays_o, float *__restrict__ rays_d,
                                                        float *__restrict__ viewdirs, float *__restrict__ radii) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
@@ -627,6 +663,18 @@ int xrb_mip_resample(const float *z_vals, const float *weights, const float *u, 
     XRB_REQUIRE(z_vals && weights && z_out, "mip_resample: null pointer");
     mip_resample_kernel<<<(n_rays + PDF_WARPS - 1) / PDF_WARPS, PDF_WARPS * 32, 0, (cudaStream_t)stream>>>(n_rays, n_samples, resample_padding, z_vals, weights, u, z_out);
     return check_launch("mip_resample");
+}
+
+int xrb_ngp_batch_sample(const float *poses, const float *images_rgba, int n_images, int H, int W, float fx, float fy, float cx, float cy, const int64_t *row_idx, int64_t n,
+                         const float *u_bg, uint64_t seed, int64_t n_prior_calls, float *rays_o, float *rays_d, float *target_s, float *alpha, float *img_ids, float *bg_color, void *stream) {
+    XRB_REQUIRE(n_images >= 1 && H >= 1 && W >= 1 && n >= 0, "ngp_batch_sample: bad arguments");
+    if (n == 0) return XRB_OK;
+    XRB_REQUIRE(poses && images_rgba && row_idx && rays_o && rays_d && target_s && alpha && img_ids && bg_color, "ngp_batch_sample: null pointer");
+    XRB_REQUIRE(((uintptr_t)images_rgba & 15) == 0, "ngp_batch_sample: images must be 16-byte aligned");
+    int64_t blocks = (n + 255) / 256; if (blocks > NUM_SMS * 16) blocks = NUM_SMS * 16;
+    ngp_batch_sample_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(poses, images_rgba, n_images, H, W, fx, fy, cx, cy, row_idx, n, u_bg, host_rng(seed, n_prior_calls), rays_o, rays_d,
+                                                                          target_s, alpha, img_ids, bg_color);
+    return check_launch("ngp_batch_sample");
 }
 
 int xrb_nerf_get_rays(const float *c2w_host, int H, int W, float fx, float fy, float cx, float cy, int convention, const int32_t *pixel_idx, int64_t n, float *rays_o, float *rays_d,

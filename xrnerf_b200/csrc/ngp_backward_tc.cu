@@ -310,6 +310,10 @@ __global__ void __launch_bounds__(256, 1) ngp_field_bwd_tc_kernel(HashGridDev g,
         }
         // ------------------------------------------------ hash-table gradient scatter
         if (valid && !(dbg & 9)) {
+            // The scatter is bound by the LSU's reduction issue rate (~1.3 cycles per lane and RED, measured: 450 of 880 us per 700 K samples with 128 two-float
+            // REDs per sample), so x-adjacent corners that are also adjacent in memory go out as ONE 16-byte red.global.add.v4.f32:
+            //   hashed level: entries of (gx, y, z) and (gx^1, y, z) are the two halves of an aligned 16-byte pair -> even gx: 4 v4 instead of 8 v2
+            //   dense level : idx and idx + 1 -> one v4 when idx is even (and the pair does not wrap at the table end)
 #pragma unroll 1
             for (int l = 0; l < 16; ++l) {
                 const uint32_t hs = g.offset[l + 1] - g.offset[l], res = g.res[l];
@@ -324,11 +328,22 @@ __global__ void __launch_bounds__(256, 1) ngp_field_bwd_tc_kernel(HashGridDev g,
 #pragma unroll
                 for (int q = 0; q < 16; ++q) if (q == l) { g0 = genc[2 * q]; g1 = genc[2 * q + 1]; }   // register array indexed by the rolled loop counter: select, never spill
                 g0 *= (1.f / BT_SCALE); g1 *= (1.f / BT_SCALE);
+                const bool hashed = (g.hashed_mask >> l) & 1u;
 #pragma unroll
-                for (int cn = 0; cn < 8; ++cn) {
-                    float w = ((cn & 1) ? fx : 1.f - fx) * ((cn & 2) ? fy : 1.f - fy) * ((cn & 4) ? fz : 1.f - fz);
-                    uint32_t idx = grid_index(ix + (cn & 1), iy + ((cn >> 1) & 1), iz + ((cn >> 2) & 1), hs, res);
-                    atomicAdd(tl + idx, make_float2(w * g0, w * g1));
+                for (int yz = 0; yz < 4; ++yz) {
+                    const float wyz = ((yz & 1) ? fy : 1.f - fy) * ((yz & 2) ? fz : 1.f - fz);
+                    const float w0 = (1.f - fx) * wyz, w1 = fx * wyz;
+                    const uint32_t i0 = grid_index(ix, iy + (yz & 1), iz + (yz >> 1), hs, res), i1 = grid_index(ix + 1u, iy + (yz & 1), iz + (yz >> 1), hs, res);
+                    const bool pair = hashed ? ((ix & 1u) == 0u) : (((i0 & 1u) == 0u) && i1 == i0 + 1u);   // hashed, even gx: i1 == i0 ^ 1; both cases: i0 even, i1 = i0 + 1... or i0 odd (hashed)
+                    if (pair) {
+                        const uint32_t lo = i0 & ~1u;                      // hashed level with an odd i0: the pair is (i1, i0) in memory order
+                        const bool swap = (i0 & 1u) != 0u;
+                        const float a0 = swap ? w1 : w0, a1 = swap ? w0 : w1;
+                        atomicAdd(reinterpret_cast<float4 *>(tl + lo), make_float4(a0 * g0, a0 * g1, a1 * g0, a1 * g1));
+                    } else {
+                        atomicAdd(tl + i0, make_float2(w0 * g0, w0 * g1));
+                        atomicAdd(tl + i1, make_float2(w1 * g0, w1 * g1));
+                    }
                 }
             }
         }
@@ -382,7 +397,7 @@ int xrb_ngp_mlp_backward_tc(const xrb_ngp_config *cfg, const xrb_ngp_table *tabl
     XRB_REQUIRE(n >= 0 && pts_stride >= 3 && dirs_stride >= 3, "ngp_mlp_backward_tc: bad size");
     if (n == 0) return XRB_OK;
     XRB_REQUIRE(table && weight_image && pts && dirs && dl_draw && d_table && d_density && d_color, "ngp_mlp_backward_tc: null pointer");
-    XRB_REQUIRE(((uintptr_t)dl_draw & 15) == 0 && ((uintptr_t)d_table & 7) == 0 && ((uintptr_t)weight_image & 15) == 0, "ngp_mlp_backward_tc: dl_draw / weight image must be 16-byte, d_table 8-byte aligned");
+    XRB_REQUIRE(((uintptr_t)dl_draw & 15) == 0 && ((uintptr_t)d_table & 15) == 0 && ((uintptr_t)weight_image & 15) == 0, "ngp_mlp_backward_tc: dl_draw, d_table and the weight image must be 16-byte aligned");
     if (!((cfg->density_hidden == 1 && cfg->color_hidden == 1) || (cfg->density_hidden == 1 && cfg->color_hidden == 2))) {
         set_error("ngp_mlp_backward_tc: tensor-core backward is built for (density_hidden, color_hidden) = (1,1) or (1,2); use xrb_ngp_mlp_backward");
         return XRB_E_UNSUPPORTED;

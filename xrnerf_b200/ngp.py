@@ -22,9 +22,10 @@ class NgpField(nn.Module):
     def __init__(self, n_levels=16, n_features=2, log2_hashmap_size=19, base_resolution=16, per_level_scale=PER_LEVEL_SCALE, width=64,
                  density_hidden=1, color_hidden=2, seed=1337, impl=1, n_packed_levels=None):
         super().__init__()
-        # levels [0, n_packed_levels) are gathered from the cell image (xrb_ngp_table, include/xrnerf_b200.h): 6 = the five dense levels + the
-        # first hashed one, 27.6 MB; 0 disables the image
-        self.n_packed = int(os.environ.get('XRB_PACKED_LEVELS', '6')) if n_packed_levels is None else int(n_packed_levels)
+        # levels [0, n_packed_levels) are gathered from the cell image (xrb_ngp_table, include/xrnerf_b200.h): 7 = the five dense levels + the first two hashed
+        # ones, 72.5 MB (L2-resident next to the 24.4 MB table); the trainer drops to 6 (27.6 MB: the image is rebuilt after every optimiser step); 0 disables it.
+        # Deeper images (up to 13 levels, 25 GB) are served by HBM and measured slower.
+        self.n_packed = int(os.environ.get('XRB_PACKED_LEVELS', '7')) if n_packed_levels is None else int(n_packed_levels)
         self.cfg = _C.NgpConfig(n_levels, n_features, log2_hashmap_size, base_resolution, per_level_scale, width, density_hidden, color_hidden)
         n_hash = _C.lib.xrb_tcnn_hashgrid_num_params(self.cfg)
         if n_hash < 0:
@@ -62,6 +63,13 @@ class NgpField(nn.Module):
         nb = _C.lib.xrb_ngp_cell_image_bytes(self.cfg, self.n_packed) if self.n_packed > 0 else 0
         self._cells = torch.empty(nb, dtype=torch.uint8, device=dev) if nb else None
         self.tab = _C.NgpTable(self._table16.data_ptr(), self._cells.data_ptr() if nb else None, self.n_packed if nb else 0)
+
+    def set_packed_levels(self, n):
+        """change how many levels the cell image holds (re-allocates and rebuilds it on the next refresh)"""
+        if int(n) != self.n_packed:
+            self.n_packed = int(n)
+            self._table16 = None
+            self.mark_dirty()
 
     def rebuild_cells(self):
         """cell image <- fp16 table (one kernel; called whenever the table changed)"""

@@ -52,8 +52,9 @@ def sample_pdf(data, N_samples, is_perturb=False, is_test=False):
     return data
 
 
-def resample_along_rays(data, randomized, ray_shape, resample_padding):
-    """mip.py:146-176 as one kernel (blur + piecewise-constant inverse CDF)."""
+def resample_along_rays(data, randomized, ray_shape, resample_padding, rand=None):
+    """mip.py:146-176 as one kernel (blur + piecewise-constant inverse CDF). `rand`: the [n, S+1] uniforms the reference draws with torch.rand when
+    `randomized` (mip.py:31-33); default: drawn on the device."""
     if ray_shape != 'cone':
         raise NotImplementedError('ray_shape cone (the reference configs)')
     z, w = data['z_vals'].contiguous().float(), data['weights'].detach().contiguous().float()
@@ -61,7 +62,8 @@ def resample_along_rays(data, randomized, ray_shape, resample_padding):
     u = None
     if randomized:
         sdt = 1.0 / s1
-        u = torch.arange(s1, device=z.device) * sdt + torch.rand((n, s1), device=z.device) * (sdt - torch.finfo(torch.float32).eps)
+        r = torch.rand((n, s1), device=z.device) if rand is None else rand.to(z.device).float()
+        u = torch.arange(s1, device=z.device) * sdt + r * (sdt - torch.finfo(torch.float32).eps)
         u = torch.minimum(u, torch.tensor(1. - torch.finfo(torch.float32).eps, device=z.device)).contiguous()
     z_new = torch.empty_like(z)
     _C.check(_C.lib.xrb_mip_resample(_C.ptr(z), _C.ptr(w), _C.ptr(u), n, s1 - 1, float(resample_padding), _C.ptr(z_new), _C.stream()), 'mip_resample')
