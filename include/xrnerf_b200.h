@@ -320,6 +320,45 @@ int xrb_ngp_batch_sample(const float *poses, const float *images_rgba, int n_ima
 /* GetZvals (create.py:502-531, near/far constants) and, with u f32[n_rays, S] != NULL, PerturbZvals (augment.py:269-283) */
 int xrb_nerf_zvals(int64_t n_rays, int n_samples, float near_, float far_, int lindisp, const float *u, float *z_vals, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * NerfMLP training on tensor cores (csrc/nerf_train.cu): what torch.autograd + cuBLAS do for the reference's NerfMLP (xrnerf/models/mlps/nerf_mlp.py:70-94,
+ * trained by networks/nerf.py:71-92 / networks/mipnerf.py:45-74) as UMMA kernels over TILE IMAGES (per 128-row tile, C/64 blocks of [128 x 64] fp16 in the
+ * K-major 128-byte-swizzle layout: the encoders' output format, xrb_nerf_enc_image_bytes). The host (xrnerf_b200/nerf_train.py) strings the layers together.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    /* A operand: up to two sources, concatenated block-wise (e.g. the skip layer: point-encoding block + 4 hidden blocks); <= 5 blocks in total */
+    const void *a_base[2]; uint32_t a_tile_stride[2]; uint32_t a_blk_off[2]; int a_n_blk[2]; int n_a;
+    const void *w;                       /* weight slabs (xrb_nerf_tg_pack_weights) */
+    /* per weight slab: byte offset in w, bytes (<= 32768), MMA groups using it (A block a_blk0 + j), K-steps of 16 per group (1..4), accumulator column, first-writer flag */
+    uint32_t slab_w_off[10]; uint32_t slab_bytes[10]; int slab_n_sub[10]; int slab_a_blk0[10]; int slab_d_col[10]; int slab_first[10]; int slab_n_k[10]; int n_slabs;
+    int b_mn;                            /* 0: slabs read K-major (forward: Y = A . W^T); 1: MN-major (input gradient: dX = dZ . W, same slabs) */
+    int mma_n;                           /* N of every MMA: the layer width (forward) or 64 (input gradient) */
+    int out_cols;                        /* accumulator columns read back (16, 128 or 256) */
+    int epi;                             /* 0: + bias, ReLU (relu != 0), fp16 -> y image; 1: + bias -> fp32 yf[row * yf_stride + yf_col + k] * yf_scale, k < yf_n;
+                                            2: * [x > 0] -> fp16 y image (x: activation image, out_cols/64 blocks); 3: fp16 -> y image */
+    int relu; const float *bias;
+    const void *x_base; uint32_t x_tile_stride; uint32_t x_blk_off;
+    void *y; uint32_t y_tile_stride; uint32_t y_blk_off;
+    float *yf; int yf_stride; int yf_col; int yf_n; float yf_scale;
+    int64_t n_rows;
+} xrb_tg_layer;
+int xrb_nerf_tg_layer(const xrb_tg_layer *layer, void *stream);
+/* weight gradient of one layer and one input source: dW[N][K] (fp32, ACCUMULATED) [:, k_off : k_off + k_cols] += dZ^T . X over all rows; db[N] += column sums of dZ
+ * when db != NULL. z: dZ image (N/64 blocks per tile, 1 block for N <= 16), x: input image source (1..4 blocks). Gradients are unscaled by xrb_nerf_tg_grad_scale(). */
+typedef struct {
+    const void *z_base; uint32_t z_tile_stride; uint32_t z_blk_off;
+    const void *x_base; uint32_t x_tile_stride; uint32_t x_blk_off; int x_n_blk;
+    int N, K, k_off, k_cols;
+    float *dW; float *db;
+    int64_t n_rows;
+} xrb_tg_dw;
+int xrb_nerf_tg_dw(const xrb_tg_dw *layer, void *stream);
+/* nn.Linear weight W[N][K_in] (fp32) -> n_kb slabs [n_pad x 64] fp16 (n_pad = N rounded up to 16): slab kb holds input columns [col0[kb], + valid[kb]) (zero beyond) */
+int xrb_nerf_tg_pack_weights(const float *W, int N, int K_in, int n_pad, int n_kb, const int *col0_host, const int *valid_host, void *slabs, void *stream);
+/* dL/draw f32[n_rows,4] -> the two one-block dZ images of the output heads (d rgb in columns 0..2, d alpha in column 0), scaled by xrb_nerf_tg_grad_scale() */
+int xrb_nerf_tg_pack_draw(const float *d_raw, int64_t n_rows, void *z_rgb_image, void *z_alpha_image, void *stream);
+float xrb_nerf_tg_grad_scale(void);
+
 /* Measurement utility (bench.py's second roofline; no reference counterpart): random reads of 4-, 8- or 32-byte records from a table (L2-resident when
  * it is the size of the fp16 hash table) by SMs x 8 CTAs x 256 threads, `rounds` rounds of 8 independent loads per thread. *loads_issued (host) receives the
  * number of loads of the launch; every 4/8-byte load costs one 32-byte sector, which is what bounds the hash gather. */

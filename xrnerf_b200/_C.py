@@ -92,6 +92,11 @@ _SIGS = {
     'xrb_mip_resample': (_i, [P, P, P, _i, _i, _f, P, P]),
     'xrb_nerf_get_rays': (_i, [C.POINTER(C.c_float), _i, _i, _f, _f, _f, _f, _i, P, _i64, P, P, P, P, P]),
     'xrb_ngp_batch_sample': (_i, [P, P, _i, _i, _i, _f, _f, _f, _f, P, _i64, P, _u64, _i64, P, P, P, P, P, P, P]),
+    'xrb_nerf_tg_layer': (_i, [P, P]),
+    'xrb_nerf_tg_dw': (_i, [P, P]),
+    'xrb_nerf_tg_pack_weights': (_i, [P, _i, _i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int), P, P]),
+    'xrb_nerf_tg_pack_draw': (_i, [P, _i64, P, P, P]),
+    'xrb_nerf_tg_grad_scale': (C.c_float, []),
     'xrb_micro_gather': (_i, [P, _i64, _i, _i, C.POINTER(C.c_int64), P, P]),
     'xrb_nerf_zvals': (_i, [_i64, _i, _f, _f, _i, P, P, P]),
     'xrb_ngp_render': (_i, [_cfg, _tab, P, P, P, P, _i, _i, _f, _f, _f, _f, _u64, _i64, C.POINTER(C.c_float), _i, _i, P, P, P, P, P, P, P, P]),

@@ -20,9 +20,9 @@ class NerfMLP(BaseMLP):
     """8x256 ReLU MLP with skip at layer 4 and a 128-wide view branch; parameters are nn.Linear modules with the reference's
     names (pts_linears.i, views_linears.0, feature_linear, alpha_linear, rgb_linear) so reference checkpoints load.
 
-    Inference (no_grad) runs the whole chain in ONE persistent tcgen05 kernel (csrc/nerf_mlp_tc.cu; fp16 operands, fp32 accumulate).
-    With autograd enabled (training) the dense layers are library GEMMs (cuBLAS through torch, fp32) — the tensor-core backward is not
-    written yet."""
+    Inference (no_grad) runs the whole chain in ONE persistent tcgen05 kernel (csrc/nerf_mlp_tc3.cu; fp16 operands, fp32 accumulate).
+    With autograd enabled (training) run_mlp is ONE autograd node whose forward and backward are UMMA kernels over fp16 tile images
+    (xrnerf_b200/nerf_train.py, csrc/nerf_train.cu); `fused_train = False` (or an unsupported shape) falls back to nn.Linear under autograd."""
 
     def __init__(self, skips=[4], netdepth=8, netwidth=256, output_ch=4, use_viewdirs=True, netchunk=1024 * 32, embedder=None, fused=True, **kwarg):
         super().__init__()
@@ -77,6 +77,10 @@ class NerfMLP(BaseMLP):
             from ..nerf_mlp import nerf_mlp_forward
             image, bias = self._packed()
             return nerf_mlp_forward(image, bias, x, self.input_ch, self.input_ch_dirs, version=self.kernel_version)
+        if self.fused and getattr(self, 'fused_train', True) and torch.is_grad_enabled() and x.is_cuda and any(p.requires_grad for p in self.parameters()):
+            from .. import nerf_train
+            if nerf_train.supported(self):   # training: every dense layer forward + backward as UMMA kernels over fp16 tile images (csrc/nerf_train.cu), one autograd node
+                return nerf_train.run_mlp_train(self, x)
         if self.chunk is None:
             return self.run_mlp(x)
         return torch.cat([self.run_mlp(x[i:i + self.chunk]) for i in range(0, x.shape[0], self.chunk)], 0)
