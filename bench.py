@@ -663,8 +663,8 @@ def run_ours(args):
         except Exception as e:   # an auxiliary arm must never take the headline line down
             nerf = {'error': repr(e)[:300]}
 
-    # ---- NeRF training step (configs[2], N_rand 4096 as configs/nerf/nerf_blender_base01.py): our encoders / composite fwd+bwd / sample_pdf kernels under autograd;
-    # the 8x256 GEMM chain and its backward run on library GEMMs (fp32) - the tensor-core backward is not written yet
+    # ---- NeRF training step (configs[2], N_rand 4096 as configs/nerf/nerf_blender_base01.py): encoders / composite fwd+bwd / sample_pdf kernels + the 12 dense layers of both
+    # networks forward AND backward as UMMA kernels over fp16 tile images (csrc/nerf_train.cu), torch.optim.Adam on the fp32 nn.Linear parameters
     nerf_train = None
     if not args.no_nerf:
         try:
@@ -674,10 +674,10 @@ def run_ours(args):
                                         render=dict(type='NerfRender', white_bkgd=True, raw_noise_std=0))).to(dev)
             topt = torch.optim.Adam(tnet.parameters(), lr=5e-4, betas=(0.9, 0.999))
             n_t = 4096
-            o_t, d_t = dev_batches[0][0][:n_t].contiguous(), dev_batches[0][1][:n_t].contiguous()
+            o_t, d_t, v_t = nerf_convention_rays(dev, n_t, 900 + rank)
             tt = torch.linspace(0., 1., 64, device=dev)
             z_t = (2.0 * (1. - tt) + 6.0 * tt).expand(n_t, 64).contiguous()
-            tdata = {'rays_o': o_t[None], 'rays_d': d_t[None], 'viewdirs': d_t[None], 'z_vals': z_t[None], 'pts': (o_t[:, None, :] + d_t[:, None, :] * z_t[:, :, None])[None],
+            tdata = {'rays_o': o_t[None], 'rays_d': d_t[None], 'viewdirs': v_t[None], 'z_vals': z_t[None], 'pts': (o_t[:, None, :] + d_t[:, None, :] * z_t[:, :, None])[None],
                      'target_s': torch.rand((1, n_t, 3), device=dev)}
 
             def tstep():
@@ -697,10 +697,55 @@ def run_ours(args):
             if world > 1:
                 dist.all_reduce(qm, op=dist.ReduceOp.MAX)
             nerf_train = {'value': world * n_t * KT / (float(qm.item()) * 1e-3), 'unit': 'rays/s', 'ms_per_step': float(qm.item()) / KT, 'rays_per_step_per_gpu': n_t,
-                          'what': 'NerfNetwork.train_step + Adam (per-rank, no gradient all-reduce in this arm): fused encoders / composite fwd+bwd / sample_pdf kernels, dense layers on library fp32 GEMMs under autograd'}
+                          'rows_per_step_per_gpu': n_t * (64 + 192), 'flop_per_step': 3 * n_t * (64 + 192) * 593408 * 2,
+                          'tflops': 3 * n_t * (64 + 192) * 593408 * 2 / (float(qm.item()) / KT * 1e-3) / 1e12,
+                          'what': 'NerfNetwork.train_step + Adam (per-rank, no gradient all-reduce in this arm): encoders / composite fwd+bwd / sample_pdf kernels; the dense layers of both '
+                                  'networks forward + backward on tcgen05 (tile-image GEMM kernels: forward, input gradient with fused ReLU mask, weight gradient accumulated in TMEM)'}
             del tnet, topt, tdata
         except Exception as e:   # an auxiliary arm must never take the headline line down
             nerf_train = {'error': repr(e)[:300]}
+
+    # ---- Mip-NeRF training step (configs[3]: 2 levels x 128 samples through the SAME MLP, loss = fine + 0.1 coarse, mipnerf.py:45-74), 4096 rays per step
+    mip_train = None
+    if not args.no_mip:
+        try:
+            from xrnerf_b200 import registry as R
+            mtnet = R.build_network(dict(type='MipNerfNetwork', cfg=dict(phase='train', ray_shape='cone', resample_padding=0.01, use_multiscale=False, coarse_loss_mult=0.1, num_levels=2,
+                                                                         chunk=1024 * 32, bs_data='rays_o'),
+                                         mlp=dict(type='NerfMLP', skips=[4], netdepth=8, netwidth=256, netchunk=1024 * 32, use_viewdirs=True,
+                                                  embedder=dict(type='MipNerfEmbedder', min_deg_point=0, max_deg_point=16, min_deg_view=0, max_deg_view=4, use_viewdirs=True, append_identity=True)),
+                                         render=dict(type='MipNerfRender', white_bkgd=True, raw_noise_std=0, rgb_padding=0.001, density_bias=-1, density_activation='softplus'))).to(dev)
+            mtopt = torch.optim.Adam(mtnet.parameters(), lr=5e-4, betas=(0.9, 0.999))
+            n_mt = 4096
+            o_m, d_m, v_m, r_m = nerf_convention_rays(dev, n_mt, 950 + rank, with_radii=True)
+            tm_ = torch.linspace(0., 1., 129, device=dev)
+            z_m = (2.0 * (1. - tm_) + 6.0 * tm_).expand(n_mt, 129).contiguous()
+            mdata = {'rays_o': o_m[None], 'rays_d': d_m[None], 'viewdirs': v_m[None], 'radii': r_m[None], 'lossmult': torch.ones((1, n_mt, 1), device=dev), 'z_vals': z_m[None],
+                     'target_s': torch.rand((1, n_mt, 3), device=dev)}
+
+            def mstep():
+                out = mtnet.train_step(dict(mdata), mtopt)
+                mtopt.zero_grad(set_to_none=True); out['loss'].backward(); mtopt.step()
+            for _ in range(2):
+                mstep()
+            barrier()
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            KMT = 5
+            w0.record()
+            for _ in range(KMT):
+                mstep()
+            w1.record()
+            barrier()
+            wm = torch.tensor([w0.elapsed_time(w1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(wm, op=dist.ReduceOp.MAX)
+            mip_train = {'value': world * n_mt * KMT / (float(wm.item()) * 1e-3), 'unit': 'rays/s', 'ms_per_step': float(wm.item()) / KMT, 'rays_per_step_per_gpu': n_mt,
+                         'rows_per_step_per_gpu': n_mt * 256, 'tflops': 3 * n_mt * 256 * 610304 * 2 / (float(wm.item()) / KMT * 1e-3) / 1e12,
+                         'what': 'MipNerfNetwork.train_step + Adam: cast_rays + IPE + composite fwd/bwd + resample kernels; the MLP (both levels) forward + backward on tcgen05 tile-image GEMMs'}
+            del mtnet, mtopt, mdata
+        except Exception as e:
+            import traceback
+            mip_train = {'error': repr(e)[:300], 'trace': traceback.format_exc()[-500:]}
 
     # ---- Mip-NeRF arm (BASELINE configs[3]: 2 levels x 128 cone samples, IPE): the same tcgen05 NerfMLP on IPE tile images, device-resident rays
     mip = None
@@ -831,6 +876,7 @@ def run_ours(args):
             'nerf': nerf,
             'nerf_train': nerf_train,
             'mip': mip,
+            'mip_train': mip_train,
             'all_ones_grid': all_ones,
             'train': train,                                   # last on purpose: the driver keeps the tail of the line
         }
