@@ -501,21 +501,24 @@ def run_ours(args):
                 tr.step(*nb(i), tgt, bgc, next_rays=nb(i + 1))
             barrier()
             t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            trained = torch.zeros((), dtype=torch.int64, device=dev)
+            torch.cuda.synchronize()
+            trained0 = int(tr.trained_total.item())                     # batches prepared so far (warm-up + the first timed batch, prepared one step ahead)
             t0e.record()
+            th_ = time.perf_counter()
             for i in range(K):
                 tr.step(*nb(W + i), tgt, bgc, next_rays=nb(W + i + 1))
-                trained += tr.trained_rays()
+            host_issue_ms = (time.perf_counter() - th_) * 1e3 / K       # host time to ENQUEUE a step (no sync inside): above ms_per_step means the step is launch-bound
             t1e.record()
             barrier()
             tm = torch.tensor([t0e.elapsed_time(t1e)], dtype=torch.float64, device=dev)
-            tsum = trained.double().reshape(1)
+            # K batches were prepared (one step ahead) inside the loop: their fully-trained ray count is what the device counter gained
+            tsum = torch.tensor([float(int(tr.trained_total.item()) - trained0)], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tm, op=dist.ReduceOp.MAX)
                 dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
             train = {'value': float(tsum.item()) / (float(tm.item()) * 1e-3), 'unit': 'rays/s (trained rays only)', 'ms_per_step': float(tm.item()) / K,
                      'rays_per_step': world * N_RAYS, 'trained_rays_per_step': float(tsum.item()) / K, 'target_batch_size': T_TRAIN,
-                     'compacted_samples_per_step_rank0': int(tr.compacted_samples().item()), 'grad_comm': tr.grad_comm, 'field_backward': 'tcgen05' if tr.bwd_impl == 1 else 'cuda cores',
+                     'compacted_samples_per_step_rank0': int(tr.compacted_samples().item()), 'grad_comm': tr.grad_comm, 'host_issue_ms_per_step': host_issue_ms, 'field_backward': 'tcgen05' if tr.bwd_impl == 1 else 'cuda cores',
                      'what': 'march + compaction (aux stream, one step ahead) | field fwd (tcgen05) + composite fwd + Huber x5 + composite bwd + field bwd (tcgen05 dX/dW) + gradient exchange '
                              '(world>1: bf16 reduce-scatter -> sharded Adam -> fp16 all-gather; MLP weights fp32 all-reduce) + fused Adam over 12.2M params + cell-image refresh'}
             del tr

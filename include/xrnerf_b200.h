@@ -92,6 +92,10 @@ int xrb_rm_compacted_coord(const float *network_output, const float *coords_in, 
                            int max_compacted, float *coords_out, int32_t *numsteps_compacted, int32_t *ray_counter,
                            int32_t *step_counter, void *workspace, void *stream);
 
+/* Training bookkeeping (no reference counterpart: the reference never counts them): ADDS to *accum (device i64) the number of rays whose every marched sample
+ * survived compacted_coord's truncation (numsteps_compacted.count == numsteps.count), i.e. the rays the step really trains. */
+int xrb_ngp_count_trained_rays(const int32_t *numsteps, const int32_t *numsteps_compacted, int n_rays, int64_t *accum, void *stream);
+
 /* replaces calc_rgb_forward_api (pybind_api.h:60-72). raw f32[S,4]; coords f32[S,7]; bg f32[N,3]; rgb f32[N,3]. */
 int xrb_rm_calc_rgb_forward(const float *raw, const float *coords, const int32_t *numsteps, const int32_t *numsteps_compacted,
                             const float *bg, int n_rays, int rgb_act, int dens_act, float *rgb_out, void *stream);

@@ -47,6 +47,7 @@ _SIGS = {
     'xrb_rm_rays_sampler': (_i, [P, P, P, P, P, P, _i, _i, _f, _f, _f, _f, _u64, _i64, P, P, P, P, P, P]),
     'xrb_rm_compacted_coord_workspace': (_sz, [_i]),
     'xrb_rm_compacted_coord': (_i, [P, P, P, _i, _i, P, P, P, P, P, P]),
+    'xrb_ngp_count_trained_rays': (_i, [P, P, _i, P, P]),
     'xrb_rm_calc_rgb_forward': (_i, [P, P, P, P, P, _i, _i, _i, P, P]),
     'xrb_rm_calc_rgb_backward': (_i, [P, P, P, P, P, P, _i, _i, _i, P, P]),
     'xrb_rm_calc_rgb_inference': (_i, [P, P, P, C.POINTER(C.c_float), _i, _i, _i, P, P, P]),

@@ -242,6 +242,15 @@ __global__ void __launch_bounds__(256) compact_copy_kernel(int n_rays, uint32_t 
     for (uint32_t k = lane; k < nc * 7; k += 32) dst[k] = src[k];
 }
 
+// rays of a compacted batch whose every marched sample survived the compaction (numsteps_c.count == numsteps.count): the rays a training step really trains
+__global__ void __launch_bounds__(256) count_trained_kernel(int n_rays, const int32_t *__restrict__ numsteps, const int32_t *__restrict__ numsteps_c, unsigned long long *__restrict__ accum) {
+    unsigned int local = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rays; i += gridDim.x * blockDim.x) local += numsteps_c[2 * (size_t)i] == numsteps[2 * (size_t)i] ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(accum, (unsigned long long)local);
+}
+
 // ============================================================================ compositing (calc_rgb.cu)
 __device__ __forceinline__ float warp_excl_prod(float v, int lane, float *incl_out) {
     float incl = v;
@@ -548,6 +557,15 @@ int xrb_rm_compacted_coord(const float *network_output, const float *coords_in, 
     int blocks = (int)(((size_t)n_rays * 32 + 255) / 256);
     compact_copy_kernel<<<blocks, 256, 0, s>>>(n_rays, (uint32_t)max_compacted, coords_in, numsteps, w.local_excl, w.block_sum, w.misc, coords_out, numsteps_compacted, ray_counter);
     return check_launch("compacted_coord");
+}
+
+int xrb_ngp_count_trained_rays(const int32_t *numsteps, const int32_t *numsteps_compacted, int n_rays, int64_t *accum, void *stream) {
+    XRB_REQUIRE(n_rays >= 0, "count_trained_rays: negative size");
+    if (n_rays == 0) return XRB_OK;
+    XRB_REQUIRE(numsteps && numsteps_compacted && accum && ((uintptr_t)accum & 7) == 0, "count_trained_rays: null / misaligned pointer");
+    int blocks = (n_rays + 255) / 256; if (blocks > NUM_SMS * 4) blocks = NUM_SMS * 4;
+    count_trained_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(n_rays, numsteps, numsteps_compacted, (unsigned long long *)accum);
+    return check_launch("count_trained_rays");
 }
 
 int xrb_rm_calc_rgb_forward(const float *raw, const float *coords, const int32_t *numsteps, const int32_t *numsteps_compacted, const float *bg, int n_rays, int rgb_act,

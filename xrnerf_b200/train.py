@@ -193,6 +193,7 @@ class NgpTrainer:
         self.loss_accum = torch.zeros(1, dtype=torch.float32, device=dev)
         self.grid_mean = torch.ones(1, dtype=torch.float32, device=dev)
         self.aux = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None
+        self.trained_total = torch.zeros(1, dtype=torch.int64, device=dev)    # rays fully trained, summed over every batch prepared so far (device counter, no sync)
         self.march_calls = 0
         self.cur = 0
         self.master_stale = False
@@ -220,6 +221,7 @@ class NgpTrainer:
             # compacted count from the device (cnt_c[1]).
             _C.check(_C.lib.xrb_rm_compacted_coord(None, _C.ptr(s.coords), _C.ptr(s.numsteps), n, self.T, _C.ptr(s.coords_c), _C.ptr(s.numsteps_c), _C.ptr(s.cnt_c[0:1]),
                                                    _C.ptr(s.cnt_c[1:2]), _C.ptr(s.ws_compact), st), 'compacted_coord')
+            _C.check(_C.lib.xrb_ngp_count_trained_rays(_C.ptr(s.numsteps), _C.ptr(s.numsteps_c), n, _C.ptr(self.trained_total), st), 'count_trained_rays')
             s.ready = torch.cuda.Event(); s.ready.record(self.aux)
         s.rays = (rays_o, rays_d)                      # keep the tensors alive until the kernels ran
 
@@ -297,7 +299,8 @@ class NgpTrainer:
 
     # ------------------------------------------------------------------ bookkeeping
     def trained_rays(self, slot=None):
-        """rays of the last step whose EVERY marched sample took part in the step (numsteps_c.count == numsteps.count): 0-dim device tensor"""
+        """rays of the last step whose EVERY marched sample took part in the step (numsteps_c.count == numsteps.count): 0-dim device tensor. For tests and one-off queries
+        (call it after a synchronize: the slot is re-marched by the aux stream two steps later); a training loop reads `trained_total`, which the aux stream keeps up to date."""
         s = self.slots[self.cur ^ 1 if slot is None else slot]
         return (s.numsteps_c[:, 0] == s.numsteps[:, 0]).sum()
 
