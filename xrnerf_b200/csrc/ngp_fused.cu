@@ -44,6 +44,8 @@ struct FusedParams {
     uint32_t *sched;     // [0] next ray group, [1] CTAs finished (both zero between launches)
     unsigned long long *dbg_out;   // [gridDim.x][16]: start ns, end ns, smid, tiles, 5 field-phase (warpgroup 0) and 7 producer-phase cycle sums (only written when dbg & 8)
     int dbg;             // developer ablation bits (XRB_FUSED_DBG): 1 skip the hash gather, 2 skip the MLP layers, 4 fake march (11 samples/ray)
+    // FIELD-ONLY mode (xrb_ngp_mlp_forward, shape 4): the producers read sample rows instead of marching and write raw instead of compositing
+    int field_only; const float *pts; int pts_stride; const float *dirs; int dirs_stride; int n_samples; const int32_t *n_dev; float4 *raw_out;
 };
 
 template <int FR_N_WG, int N_PROD, int N_SLOTS>
@@ -175,6 +177,73 @@ __global__ void __launch_bounds__((4 * FR_N_WG + N_PROD) * 32, 3 - FR_N_WG) ngp_
 #else
 #define PTICK(k) do { } while (0)
 #endif
+        // claim a quarter of a tile slot, write my sample's warped direction and its 16 encoded levels into the slot row, arrive (one call per 32-sample chunk, all lanes)
+        auto submit_chunk = [&](float x, float y, float z, float wd0, float wd1, float wd2) {
+            uint32_t tk = 0;
+            if (lane == 0) tk = atomicAdd(&ctl->ticket, 1u);
+            tk = __shfl_sync(0xffffffffu, tk, 0);
+            const uint32_t X = tk >> 2, sub = tk & 3, s = X % N_SLOTS, r = X / N_SLOTS;
+            if (lane == 0) { spin_until_ge(&ctl->rounds_done[s], r); __threadfence_block(); ctl->owner[s][sub] = (pw << 1) | (n_submitted & 1); }
+            __syncwarp();
+            PTICK(5);
+            uint8_t *rowp = slots + (size_t)s * FR_SLOT_BYTES + (size_t)(sub * 32 + lane) * FR_ROW_BYTES;
+            *reinterpret_cast<float4 *>(rowp + 64) = make_float4(wd0, wd1, wd2, 0.f);
+            // hash encoding of my sample, level by level into the slot row (invalid lanes gather the cell of (0.5,0.5,0.5): L1 hits)
+            if (P.dbg & 1) {
+                for (int l = 0; l < 16; ++l) *reinterpret_cast<uint32_t *>(rowp + 4 * l) = pack_h2(x, y);
+            } else if (P.np > 0) {   // two ROLLED loops (see the file header), each with ONE gather form when the static plan holds
+#pragma unroll 1
+                for (int l = 0; l < P.np; ++l) {
+                    const float2 f = hash_level(P.table, P.cells, P.g, l, x, y, z, GATHER_PACKED);
+                    *reinterpret_cast<uint32_t *>(rowp + 4 * l) = pack_h2(f.x, f.y);
+                }
+#pragma unroll 1
+                for (int l = P.np; l < 16; ++l) {
+                    const float2 f = hash_level(P.table, P.cells, P.g, l, x, y, z, GATHER_HASHED);
+                    *reinterpret_cast<uint32_t *>(rowp + 4 * l) = pack_h2(f.x, f.y);
+                }
+            } else {
+#pragma unroll 1
+                for (int l = 0; l < 16; ++l) {
+                    const float2 f = hash_level(P.table, P.cells, P.g, l, x, y, z, GATHER_RUNTIME);
+                    *reinterpret_cast<uint32_t *>(rowp + 4 * l) = pack_h2(f.x, f.y);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(ctl->full + s);
+        };
+        if (P.field_only) {
+            // ---- FIELD-ONLY producers: 32-sample chunks from a global counter; lane = sample. The results of chunk k come back through the mailbox while
+            // chunk k+1 is being gathered, exactly as in the render mode.
+            int n = P.n_samples;
+            if (P.n_dev) n = min(n, max(*P.n_dev, 0));
+            bool pending = false, prev_valid = false; int prev_q = 0;
+            // chunks are dealt out statically (warp w of the grid takes chunks w, w + W, ...): uniform work, no scheduler word, no workspace
+            const uint32_t n_pw = gridDim.x * N_PROD;
+            for (uint32_t chunk = blockIdx.x * N_PROD + pw;; chunk += n_pw) {
+                const bool have_chunk = (uint64_t)chunk * 32 < (uint64_t)n;
+                int q = 0; bool valid = false;
+                if (have_chunk) {
+                    q = (int)(chunk * 32u + lane); valid = q < n;
+                    float x = 0.5f, y = 0.5f, z = 0.5f, wd0 = 0.5f, wd1 = 0.5f, wd2 = 0.5f;
+                    if (valid) {
+                        const float *c = P.pts + (size_t)q * P.pts_stride, *d = P.dirs + (size_t)q * P.dirs_stride;
+                        x = __ldg(c); y = __ldg(c + 1); z = __ldg(c + 2); wd0 = __ldg(d); wd1 = __ldg(d + 1); wd2 = __ldg(d + 2);
+                    }
+                    submit_chunk(x, y, z, wd0, wd1, wd2);
+                }
+                if (pending) {
+                    const uint32_t kprev = n_submitted - 1;
+                    if (lane == 0) tc::mbar_wait(&ctl->mail[pw][kprev & 1], (kprev >> 1) & 1);
+                    __syncwarp();
+                    const float4 raw = *reinterpret_cast<const float4 *>(mailbox + (size_t)((pw << 1) | (kprev & 1)) * 512 + lane * 16);
+                    if (prev_valid) P.raw_out[prev_q] = raw;
+                    pending = false;
+                }
+                if (!have_chunk) break;
+                ++n_submitted; pending = true; prev_q = q; prev_valid = valid;
+            }
+        } else
         for (;;) {
             PTICK(6);
             uint32_t grp = 0;
@@ -255,42 +324,7 @@ __global__ void __launch_bounds__((4 * FR_N_WG + N_PROD) * 32, 3 - FR_N_WG) ngp_
                         if (P.dbg & 8) { if (__float_as_uint(x + y + z + dtc) == 0x7fc12345u) pc[6] += 1; }   // force the loads to have landed
 #endif
                         PTICK(1);
-                        // ---- claim a quarter of a tile slot
-                        uint32_t tk = 0;
-                        if (lane == 0) tk = atomicAdd(&ctl->ticket, 1u);
-                        tk = __shfl_sync(0xffffffffu, tk, 0);
-                        const uint32_t X = tk >> 2, sub = tk & 3, s = X % N_SLOTS, r = X / N_SLOTS;
-                        if (lane == 0) { spin_until_ge(&ctl->rounds_done[s], r); __threadfence_block(); ctl->owner[s][sub] = (pw << 1) | (n_submitted & 1); }
-                        __syncwarp();
-                        PTICK(5);
-                        uint8_t *rowp = slots + (size_t)s * FR_SLOT_BYTES + (size_t)(sub * 32 + lane) * FR_ROW_BYTES;
-                        *reinterpret_cast<float4 *>(rowp + 64) = make_float4(wd0, wd1, wd2, 0.f);
-                        // ---- hash encoding of my sample, level by level into the slot row (invalid lanes gather the cell of (0.5,0.5,0.5): L1 hits)
-                        if (P.dbg & 1) {
-                            for (int l = 0; l < 16; ++l) *reinterpret_cast<uint32_t *>(rowp + 4 * l) = pack_h2(x, y);
-                        } else {
-                            // two ROLLED loops (see the file header), each with ONE gather form when the static plan holds (P.np > 0)
-                            if (P.np > 0) {
-#pragma unroll 1
-                                for (int l = 0; l < P.np; ++l) {
-                                    const float2 f = hash_level(P.table, P.cells, P.g, l, x, y, z, GATHER_PACKED);
-                                    *reinterpret_cast<uint32_t *>(rowp + 4 * l) = pack_h2(f.x, f.y);
-                                }
-#pragma unroll 1
-                                for (int l = P.np; l < 16; ++l) {
-                                    const float2 f = hash_level(P.table, P.cells, P.g, l, x, y, z, GATHER_HASHED);
-                                    *reinterpret_cast<uint32_t *>(rowp + 4 * l) = pack_h2(f.x, f.y);
-                                }
-                            } else {
-#pragma unroll 1
-                                for (int l = 0; l < 16; ++l) {
-                                    const float2 f = hash_level(P.table, P.cells, P.g, l, x, y, z, GATHER_RUNTIME);
-                                    *reinterpret_cast<uint32_t *>(rowp + 4 * l) = pack_h2(f.x, f.y);
-                                }
-                            }
-                        }
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(ctl->full + s);
+                        submit_chunk(x, y, z, wd0, wd1, wd2);
                         PTICK(2);
                     }
                     // ---- results of the previous chunk (its tile ran on the tensor core during this gather): composite
@@ -346,7 +380,7 @@ __global__ void __launch_bounds__((4 * FR_N_WG + N_PROD) * 32, 3 - FR_N_WG) ngp_
     __syncthreads();
     if (warp == 1) tc::tmem_dealloc<64 * FR_N_WG>(tmem_base);
     if ((P.dbg & 8) && threadIdx.x == 0) { unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); P.dbg_out[16 * blockIdx.x + 1] = t1; }
-    if (threadIdx.x == 0) {   // leave the scheduler words zero for the next launch
+    if (threadIdx.x == 0 && !P.field_only) {   // leave the scheduler words zero for the next launch
         __threadfence();
         if (atomicAdd(P.sched + 1, 1u) == gridDim.x - 1) { P.sched[0] = 0; P.sched[1] = 0; __threadfence(); }
     }
@@ -356,6 +390,27 @@ constexpr int FUSED_MAX_PROD_PER_SM = 24;
 // variant 0: one CTA per SM = 2 field warpgroups + 16 producers, 5 tile slots; variant 1: two CTAs per SM, each 1 field warpgroup + 8 producers,
 // 3 tile slots (batches on different streams then share every SM: the tail of one render overlaps the head of the next)
 static int fused_variant() { static int v = -1; if (v < 0) { const char *e = getenv("XRB_FUSED_VARIANT"); v = e ? atoi(e) : 0; if (v != 0 && v != 1) v = 0; } return v; }
+
+// FIELD-ONLY launch of the same kernel (HashNerfMLP.run_mlp): 16 producer warps per SM gather while the two field warpgroups run the MLPs on the tensor core, so the memory
+// phase and the tensor phase of different tiles overlap (in ngp_field_tc_kernel every warpgroup alternates between them and the ablation shows the sum: 130 + 52 us)
+int launch_field_ps(const xrb_ngp_config *cfg, const HashGridDev &g, const xrb_ngp_table *tab, const void *image, const float *pts, int pts_stride, const float *dirs, int dirs_stride, int n,
+                    const int32_t *n_dev, float *raw, cudaStream_t s) {
+    FusedParams P{};
+    P.g = g;
+    P.table = (const __half2 *)tab->table_fp16; P.cells = (const uint8_t *)tab->cell_image; P.np = plan_valid(P.g, tab->n_packed_levels) ? tab->n_packed_levels : 0;
+    P.weight_image = image; P.image_bytes = weight_image_layout(cfg->density_hidden, cfg->color_hidden).total;
+    P.density_hidden = cfg->density_hidden; P.color_hidden = cfg->color_hidden;
+    P.field_only = 1; P.pts = pts; P.pts_stride = pts_stride; P.dirs = dirs; P.dirs_stride = dirs_stride; P.n_samples = n; P.n_dev = n_dev; P.raw_out = (float4 *)raw;
+    { static const int dbg = getenv("XRB_FUSED_DBG") ? atoi(getenv("XRB_FUSED_DBG")) : 0; P.dbg = dbg & 3; }
+    int dev = 0, sms = NUM_SMS; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto k = ngp_render_fused_kernel<2, 16, 5>;
+    const size_t smem = fused_smem_bytes<2, 16, 5>(P.image_bytes);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int64_t n_chunks = ((int64_t)n + 31) / 32;
+    int grid = sms; if (n_chunks < (int64_t)grid * 16) grid = (int)((n_chunks + 15) / 16); if (grid < 1) grid = 1;
+    k<<<grid, (4 * 2 + 16) * 32, smem, s>>>(P);
+    return check_launch("ngp_mlp_forward (producer/consumer)");
+}
 
 }  // namespace xrb
 
@@ -390,6 +445,7 @@ int xrb_ngp_render_fused(const xrb_ngp_config *cfg, const xrb_ngp_table *table, 
     P.sched = (uint32_t *)workspace; P.tscratch = (float *)((uint8_t *)workspace + 256);
     P.dbg_out = (unsigned long long *)((uint8_t *)workspace + 256 + (size_t)sms * FUSED_MAX_PROD_PER_SM * 32 * FR_TCAP * sizeof(float));
     const int64_t n_groups = ((int64_t)n_rays + 31) / 32;
+    P.field_only = 0; P.pts = nullptr; P.dirs = nullptr; P.pts_stride = P.dirs_stride = 0; P.n_samples = 0; P.n_dev = nullptr; P.raw_out = nullptr;
 #define XRB_LAUNCH_FUSED(NWG, NP, NS)                                                                                                                  \
     do {                                                                                                                                               \
         auto k = ngp_render_fused_kernel<NWG, NP, NS>;                                                                                                 \

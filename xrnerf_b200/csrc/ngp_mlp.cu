@@ -347,6 +347,8 @@ int launch_field(const xrb_ngp_config *cfg, const xrb_ngp_table *tab, const void
         // another stream), 1 <2,128>, 2 <6,80>, 3 <8,64>
         static const int shape = getenv("XRB_TC_SHAPE") ? atoi(getenv("XRB_TC_SHAPE")) : (getenv("XRB_TC_REGS") && atoi(getenv("XRB_TC_REGS")) == 128 ? 1 : 0);
         static const int dbg = getenv("XRB_FIELD_DBG") ? atoi(getenv("XRB_FIELD_DBG")) : 0;
+        // shape 4: the producer/consumer kernel (ngp_fused.cu in FIELD-ONLY mode): gather warps and tensor-core warpgroups are different warps
+        if (shape == 4 && !density_only && (((uintptr_t)out) & 15) == 0) return launch_field_ps(cfg, g, tab, image, pts, pts_stride, dirs, dirs_stride, n, n_dev, out, s);
         // static gather plan: the kernel is specialised for "levels [0,NP) packed, all others hashed" (NP = 6, 7); anything else takes the run-time form
         const int npl = tab->n_packed_levels;
         const int np = (plan_valid(g, npl) && (npl == 6 || npl == 7)) ? npl : 0;
