@@ -25,14 +25,14 @@ def rm():
     return rm
 
 
-def gpu_march(rm, o, d, bf, cap, nprior=0, md=None, img=None, xf=None):
+def gpu_march(rm, o, d, bf, cap, nprior=0, md=None, img=None, xf=None, aabb=(0.0, 1.0), near=0.05, cone=1.0 / 256):
     n = o.shape[0]
     coords = torch.zeros((cap, 7), dtype=torch.float32, device='cuda')
     ridx = torch.zeros((n, 1), dtype=torch.int32, device='cuda')
     ns = torch.zeros((n, 2), dtype=torch.int32, device='cuda')
     cnt = torch.zeros(2, dtype=torch.int32, device='cuda')
     rm.reset_rng(ray_sampler=nprior)
-    rm.rays_sampler_api(dev(o), dev(d), dev(bf), None if md is None else dev(md), None if img is None else dev(img), None if xf is None else dev(xf), 0.0, 1.0, 0.05, 1.0 / 256,
+    rm.rays_sampler_api(dev(o), dev(d), dev(bf), None if md is None else dev(md), None if img is None else dev(img), None if xf is None else dev(xf), aabb[0], aabb[1], near, cone,
                         coords, ridx, ns, cnt)
     return coords.cpu().numpy(), ridx.cpu().numpy(), ns.cpu().numpy(), cnt.cpu().numpy()
 
@@ -68,6 +68,32 @@ def test_rays_sampler_dense_grid_1024_cap_and_empty(rm, port, scene):
     assert b[3][1] == 0 and (b[1] == -1).all()
     # n_rays == 0 is a no-op
     gpu_march(rm, o[:0], d[:0], bf, 16)
+
+
+@pytest.mark.parametrize('aabb,cone', [((0.0, 1.0), 0.0), ((0.0, 1.0), 1.0 / 64), ((-0.5, 1.5), 1.0 / 256), ((-3.5, 4.5), 1.0 / 256), ((0.1, 0.8), 0.0)])
+def test_rays_sampler_any_aabb_cone(rm, port, scene, aabb, cone):
+    """Which cell and cascade a tested position falls in depends on the position AND on the step at t (mip_from_dt): sparse random occupancy in EVERY cascade,
+    growing steps (cone > 0), boxes that are not the unit cube and axis-parallel rays (zero direction components), bit-exact vs the oracle. (Round 2 used this case to
+    validate three exact restructurings of the count pass - coarse culling, chain re-join, lane-split rays - none of which beat the plain kernel:
+    profiles/r02_march_experiments.md.)"""
+    rng = np.random.default_rng(5)
+    bf = np.zeros_like(scene['bitfield']).reshape(8, -1)
+    for m in range(8):                       # a few isolated occupied cells per cascade, plus the scene's own cascade 0
+        idx = rng.integers(0, bf.shape[1], 4000 if m else 400)
+        bf[m, idx] |= (1 << rng.integers(0, 8, idx.size)).astype(np.uint8)
+    bf[0] |= scene['bitfield'].reshape(8, -1)[0]
+    bf = bf.reshape(-1)
+    n = 6000
+    o = (rng.uniform(-1, 2, (n, 3)) * (aabb[1] - aabb[0]) + aabb[0]).astype(np.float32)
+    tgt = rng.uniform(aabb[0], aabb[1], (n, 3))
+    d = tgt - o; d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    d[:50, 0] = 0; d[50:100, 1] = 0; d[100:120, :2] = 0; d[100:120, 2] = 1      # axis-parallel rays: zero components in the walk
+    cap = n * 200
+    a = port.rays_sampler(o, d, bf, cap, aabb=aabb, cone=cone)
+    b = gpu_march(rm, o, d, bf, cap, aabb=aabb, cone=cone)
+    assert int(a[3][1]) > 100                                                     # the case is not vacuous
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[2], b[2]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(_bits(a[0]), _bits(b[0]))
 
 
 def test_rays_sampler_full_image_property(rm, scene):

@@ -93,7 +93,7 @@ def morton3d(x, y, z):
     return expand(x) | (expand(y) << np.uint32(1)) | (expand(z) << np.uint32(2))
 
 
-def lego_like_density_grid(seed=0, fill_value=0.5):
+def lego_like_density_grid(seed=0, fill_value=0.5, speckle=0.002):
     """float32[8*128^3] density grid in the reference's Morton/cascade layout: level 0 occupied inside a box + sphere shell
     (+ seeded speckle), coarser levels empty (the bitfield update OR-pools them). Values are multiples of 2^-10 so every
     summation order gives the same mean (see tests)."""
@@ -104,7 +104,7 @@ def lego_like_density_grid(seed=0, fill_value=0.5):
     box = (np.abs(c[..., 0]) < 0.22) & (np.abs(c[..., 1]) < 0.12) & (np.abs(c[..., 2]) < 0.10)
     r = np.linalg.norm(c - np.array([0.0, 0.0, 0.12], np.float32), axis=-1)
     shell = (r > 0.20) & (r < 0.23) & (c[..., 2] > 0.0)
-    speck = rng.random(box.shape) < 0.002
+    speck = rng.random(box.shape) < speckle   # floaters; 0 = a converged grid without any
     occ = box | shell | (speck & (np.abs(c).max(-1) < 0.4))
     grid = np.zeros(8 * 128 ** 3, np.float32)
     xs, ys, zs = np.nonzero(occ)
