@@ -195,6 +195,136 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------- GPU reference leg
+def _torch_field_fp32(pts01, dirs01, hash_params, dens_params, color_params, chunk=1 << 18):
+    """fp32 PyTorch restatement of HashNerfMLP.run_mlp (hashnerf_mlp.py:55-79) for the naive GPU path: tiny-cuda-nn is not in this image, so its hash grid (16 levels x 2,
+    T = 2^19, base 16, scale 1.3819), SH degree 4 and the two bias-free ReLU MLPs (32-64-16, 32-64-64-16) are written with torch ops. Timing stand-in only (the parity
+    oracle is oracle/tcnn_oracle.c); returns raw [n, 4] = (rgb, density)."""
+    import torch
+    dev = pts01.device
+    L, T, base, pls = 16, 1 << 19, 16, 1.38191288
+    scales, ress, offs, off = [], [], [0], 0
+    for l in range(L):
+        sc = float(np.float32(np.exp2(np.float32(l) * np.log2(np.float32(pls))) * base - 1.0))
+        res = int(np.ceil(sc)) + 1
+        n = min(((min(res ** 3, 0x7fffffff) + 7) // 8) * 8, T)
+        scales.append(sc); ress.append(res); off += n; offs.append(off)
+    table = hash_params.view(-1, 2)
+    Wd = [dens_params[:64 * 32].view(64, 32), dens_params[64 * 32:].view(16, 64)]
+    Wc = [color_params[:64 * 32].view(64, 32), color_params[64 * 32:64 * 32 + 64 * 64].view(64, 64), color_params[64 * 32 + 64 * 64:].view(16, 64)]
+    out = torch.empty((pts01.shape[0], 4), dtype=torch.float32, device=dev)
+    for a in range(0, pts01.shape[0], chunk):
+        x, dd = pts01[a:a + chunk], dirs01[a:a + chunk]
+        feats = []
+        for l in range(L):
+            hs, res = offs[l + 1] - offs[l], ress[l]
+            p = x * scales[l] + 0.5
+            fl = torch.floor(p)
+            fr = p - fl
+            g = fl.to(torch.int64)
+            acc = 0
+            for c in range(8):
+                q = g + torch.tensor([c & 1, (c >> 1) & 1, (c >> 2) & 1], device=dev)
+                w = torch.where(torch.tensor([bool(c & 1), bool(c & 2), bool(c & 4)], device=dev), fr, 1 - fr).prod(-1, keepdim=True)
+                if res ** 3 <= hs:
+                    idx = q[:, 0] + q[:, 1] * res + q[:, 2] * res * res
+                else:
+                    idx = (q[:, 0] ^ (q[:, 1] * 2654435761 & 0xffffffff) ^ (q[:, 2] * 805459861 & 0xffffffff)) & 0xffffffff
+                acc = acc + w * table[offs[l] + idx % hs]
+            feats.append(acc)
+        enc = torch.cat(feats, -1)
+        h = torch.relu(enc @ Wd[0].t()) @ Wd[1].t()
+        v = dd * 2 - 1
+        X, Y, Z = v[:, 0], v[:, 1], v[:, 2]
+        xy, xz, yz, x2, y2, z2 = X * Y, X * Z, Y * Z, X * X, Y * Y, Z * Z
+        sh = torch.stack([torch.full_like(X, 0.28209479177387814), -0.48860251190291987 * Y, 0.48860251190291987 * Z, -0.48860251190291987 * X, 1.0925484305920792 * xy,
+                          -1.0925484305920792 * yz, 0.94617469575755997 * z2 - 0.31539156525251999, -1.0925484305920792 * xz, 0.54627421529603959 * (x2 - y2),
+                          0.59004358992664352 * Y * (-3.0 * x2 + y2), 2.8906114426405538 * xy * Z, 0.45704579946446572 * Y * (1.0 - 5.0 * z2),
+                          0.3731763325901154 * Z * (5.0 * z2 - 3.0), 0.45704579946446572 * X * (1.0 - 5.0 * z2), 1.4453057213202769 * Z * (x2 - y2),
+                          0.59004358992664352 * X * (-x2 + 3.0 * y2)], -1)
+        cin = torch.cat([h[:, 1:], sh, torch.ones_like(X)[:, None]], -1)
+        c = torch.relu(torch.relu(cin @ Wc[0].t()) @ Wc[1].t()) @ Wc[2].t()
+        out[a:a + chunk, :3] = c[:, :3]; out[a:a + chunk, 3] = h[:, 0]
+    return out
+
+
+def reference_gpu_leg(dev, bf, rays, field, ours_chain_ms, ours_field_ms):
+    """the reference's own `raymarch_cuda` kernels, built unmodified for sm_100a (oracle/build_ref_cuda.py), timed on this GPU on the same 65 536-ray batch,
+    occupancy grid and weights, with the calls and allocations of the reference's Python wrappers (rays_sampler.py:20-27 zero-fills coords for n_rays x 1024 samples on every
+    call; every *_api ends in cudaDeviceSynchronize). Field: fp32 torch restatement (tcnn is not in the image). Per-op times next to ours through the identical signatures."""
+    import torch
+    sys.path.insert(0, ROOT)
+    try:
+        from oracle import build_ref_cuda
+        ref = build_ref_cuda.load_module()
+    except Exception as e:   # noqa: BLE001
+        return {'unavailable': 'reference CUDA extension failed to load: ' + repr(e)[:160]}
+    if ref is None:
+        return {'unavailable': 'oracle/_ref/cuda/raymarch_cuda_ref.so not built (python oracle/build_ref_cuda.py where /root/reference exists)'}
+    import xrnerf_b200.raymarch_cuda as ours
+    o, d = rays
+    n = o.shape[0]
+    md = torch.tensor([[0, 0, 0, 0, .5, .5, 1111., 1111., 0, 0, 0]], dtype=torch.float32, device=dev)
+    xf = torch.zeros((1, 4, 3), dtype=torch.float32, device=dev)
+    ids = torch.zeros(n, dtype=torch.int32, device=dev)
+    cap = n * BUDGET
+    bg = torch.zeros(3, dtype=torch.float32)
+
+    def timed(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    state = {}
+
+    def march(mod, stock_alloc):
+        def f():
+            if mod is ours:
+                ours.reset_rng(ray_sampler=0)
+            m = n * 1024 if stock_alloc else cap
+            coords = torch.zeros((m, 7), dtype=torch.float32, device=dev)
+            ridx = torch.zeros((n, 1), dtype=torch.int32, device=dev); ns = torch.zeros((n, 2), dtype=torch.int32, device=dev); cnt = torch.zeros(2, dtype=torch.int32, device=dev)
+            mod.rays_sampler_api(o, d, bf, md, ids, xf, 0.0, 1.0, 0.05, 1.0 / 256, coords, ridx, ns, cnt)
+            state[mod] = (coords, ns, cnt)
+        return f
+    t_ref_march_stock = timed(march(ref, True), reps=3)
+    t_ref_march = timed(march(ref, False))
+    t_our_march = timed(march(ours, False))
+    s_ref, s_our = int(state[ref][2][1]), int(state[ours][2][1])
+    coords_r, ns_r, _ = state[ref]
+    pts, dirs = coords_r[:s_ref, :3].contiguous(), coords_r[:s_ref, 4:7].contiguous()
+    with torch.no_grad():
+        hp, dp, cp = field.hash_params.detach().float(), field.density_params.detach().float(), field.color_params.detach().float()
+        t_field_torch = timed(lambda: state.__setitem__('raw', _torch_field_fp32(pts, dirs, hp, dp, cp)), reps=3)
+        raw_t = state['raw']
+        raw_o = field.run_mlp(pts, dirs).float()
+    field_err = float((raw_t - raw_o).abs().max())
+    rgb = torch.zeros((n, 3), dtype=torch.float32, device=dev); alpha = torch.zeros((n, 1), dtype=torch.float32, device=dev)
+    raw_c = raw_o.contiguous()
+    coords_c = coords_r[:s_ref].contiguous()
+    t_ref_comp = timed(lambda: ref.calc_rgb_influence_api(raw_c, coords_c, ns_r, bg, 2, 3, 0.0, 1.0, rgb, alpha))
+    rgb_ref = rgb.clone()
+    t_our_comp = timed(lambda: ours.calc_rgb_influence_api(raw_c, coords_c, ns_r, bg, 2, 3, 0.0, 1.0, rgb, alpha))
+    comp_err = float((rgb - rgb_ref).abs().max())
+    naive_ms = t_ref_march_stock + t_field_torch + t_ref_comp
+    return {'value': n / (naive_ms * 1e-3), 'unit': 'rays/s', 'ms_per_batch': naive_ms,
+            'what': 'naive GPU path on this B200, one 65 536-ray batch, sequential: reference rays_sampler (stock wrapper: coords zero-filled for n_rays x 1024 samples = 1.88 GB per call) '
+                    '+ fp32 torch restatement of the tcnn field (tcnn absent from the image) + reference calc_rgb_inference; reference kernels = extensions/ngp_raymarch built '
+                    'unmodified for sm_100a (oracle/build_ref_cuda.py)',
+            'per_op_ms': {'rays_sampler': {'reference_stock_wrapper': t_ref_march_stock, 'reference_kernel_same_capacity_as_ours': t_ref_march, 'ours': t_our_march},
+                          'field': {'torch_fp32_restatement': t_field_torch, 'ours': ours_field_ms},
+                          'calc_rgb_inference': {'reference': t_ref_comp, 'ours': t_our_comp}},
+            'ours_same_batch_sequential_ms': ours_chain_ms, 'speedup_sequential': naive_ms / ours_chain_ms,
+            'cross_check': {'samples_reference_kernel': s_ref, 'samples_ours': s_our, 'note': 'nvcc contracts the reference\'s o + t*d into FMAs (default -fmad=true); the bit-exact parity '
+                            'contract is the un-contracted CPU build of the same sources (oracle/_ref), so a handful of samples may differ here',
+                            'max_abs_raw_torch_vs_ours': field_err, 'max_abs_rgb_composite_ref_vs_ours': comp_err}}
+
+
+
 def nerf_convention_rays(dev, n, seed, with_radii=False):
     """BASELINE-convention rays for the NeRF / Mip-NeRF arms (VERDICT W9): Blender spiral pose (pose_spherical(theta, -30, 4.0), load_blender.py:22-29,72-75), 800x800 f=1111.1 camera,
     GetRays + GetViewdirs conventions (create.py:205-245,:437-448) through xrb_nerf_get_rays on `n` random pixels; near 2 / far 6 (load.py:58-59)."""
@@ -852,6 +982,12 @@ def run_ours(args):
                  'roofline': {'kernel': 'xrb::ngp_render_fused_kernel', 'bound': 'hbm', 'achieved': f_ach, 'peak': peak, 'unit': 'GB/s', 'frac': f_ach / peak,
                               'kernel_ms': fused_kernel_ms, 'kernel_share_of_step': 1.0, 'kernel_ms_note': 'events around the launch while P-1 other launches share the SMs',
                               'algorithmic_bytes_per_launch': f_bytes}}
+        ref_gpu = None
+        if world == 1 and not args.no_ref_gpu:
+            try:
+                ref_gpu = reference_gpu_leg(dev, bf, dev_batches[0], field, iso_chain_ms, iso_field_ms)
+            except Exception as e:   # noqa: BLE001
+                ref_gpu = {'error': repr(e)[:300]}
         head = fused if use_fused else chain
         line = {
             'metric': METRIC, 'value': head['value'], 'unit': 'rays/s', 'n_gpus': world, 'steps': K, 'warmup': W,
@@ -872,6 +1008,7 @@ def run_ours(args):
                              note='hash table (24.4 MB fp16) + cell image are L2-resident by design: DRAM traffic is far below the algorithmic bytes; the gather runs under the L2 sector rate '
                                   '(l2_gather_roofline: every 4-byte entry costs a 32-byte sector), not under the HBM copy peak this frac is quoted against'),
             'paths': {'chain': chain, 'fused': fused},
+            'reference_gpu': ref_gpu,
             'cpu_baseline': {'value': cpu_rate, 'unit': 'rays/s', 'cores': cores, 'kind': kind, 'sample': sample},
             'parity': parity,
             'image': image_arm,
@@ -899,6 +1036,7 @@ def main():
     ap.add_argument('--no-image', dest='no_image', action='store_true', help='skip the whole-image inference arm')
     ap.add_argument('--no-grid', dest='no_grid', action='store_true', help='skip the occupancy-grid update arm')
     ap.add_argument('--no-mip', dest='no_mip', action='store_true', help='skip the Mip-NeRF arm')
+    ap.add_argument('--no-ref-gpu', dest='no_ref_gpu', action='store_true', help='skip the GPU reference leg (reference raymarch_cuda kernels built for sm_100a, BASELINE.md B4)')
     ap.add_argument('--path', default='auto', choices=['auto', 'chain', 'fused'], help='inference path of the headline/e2e numbers: 5-launch chain, single-launch fused kernel, or the faster of the two (both are always measured)')
     ap.add_argument('--grad-comm', dest='grad_comm', default='sharded', choices=['sharded', 'allreduce'], help='gradient exchange of the training arm at world > 1')
     ap.add_argument('--pipeline', type=int, default=4, help='ray batches in flight (CUDA streams); 1 = strictly sequential steps')
