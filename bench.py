@@ -789,7 +789,43 @@ def run_ours(args):
                                 'sample': 'configs[0]: 1024 rays x 64 samples, coarse network only, numpy oracle (fp32, multi-threaded BLAS); best of 2'}
                 except Exception as e:
                     nerf_cpu = {'error': repr(e)[:200]}
-            nerf = {'value': rps, 'unit': 'rays/s', 'cpu_baseline': nerf_cpu, 'parity': nerf_parity, 'rays': 'NeRF convention (GetRays on random pixels of Blender spiral poses, radius 4), near 2 / far 6', 'workload': 'vanilla NeRF hierarchical 64 coarse + 192 fine evaluations per ray (configs[2]), 32768-ray batches, inference',
+            # BASELINE.md B3 for the dominant op: the reference's NerfMLP.batchify_run_mlp arithmetic (nerf_mlp.py:70-94: 11 nn.Linear GEMMs + 2 cat per 32 768-row chunk, cuBLAS)
+            # on this GPU, fp32 with TF32 off and on, against the single tcgen05 kernel on the same 2 097 152 embedded rows and weights
+            torch_mlp = None
+            if world == 1:
+                try:
+                    rows = 2097152
+                    xe = torch.randn((rows, 90), dtype=torch.float32, device=dev)
+                    res_t = {}
+                    old_flags = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+                    with torch.no_grad():
+                        def timed_mlp(reps):
+                            net.mlp.batchify_run_mlp(xe); torch.cuda.synchronize()
+                            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            a.record()
+                            for _ in range(reps):
+                                out = net.mlp.batchify_run_mlp(xe)
+                            b.record(); torch.cuda.synchronize()
+                            return a.elapsed_time(b) / reps, out
+                        t_tc, y_tc = timed_mlp(5)
+                        net.mlp.fused = False
+                        try:
+                            for name, flag in (('fp32', False), ('tf32', True)):
+                                torch.backends.cuda.matmul.allow_tf32 = flag; torch.backends.cudnn.allow_tf32 = flag
+                                res_t[name], y_t = timed_mlp(2)
+                                if not flag:
+                                    err_t = float((y_t - y_tc).abs().max())
+                        finally:
+                            net.mlp.fused = True
+                            torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old_flags
+                    torch_mlp = {'rows': rows, 'ms': {'torch_nn_linear_fp32': res_t['fp32'], 'torch_nn_linear_tf32': res_t['tf32'], 'ours_tcgen05_fp16': t_tc},
+                                 'speedup_vs_fp32': res_t['fp32'] / t_tc, 'speedup_vs_tf32': res_t['tf32'] / t_tc, 'max_abs_diff_vs_fp32': err_t,
+                                 'what': 'NerfMLP.batchify_run_mlp on 2 097 152 embedded rows (= 32 768 rays x 64 samples): the reference module\'s own arithmetic (nn.Linear chain, cat at the skip, '
+                                         '32 768-row chunks, cuBLAS) vs the single tcgen05 kernel; same weights, CUDA events'}
+                    del xe
+                except Exception as e:   # noqa: BLE001
+                    torch_mlp = {'error': repr(e)[:200]}
+            nerf = {'value': rps, 'unit': 'rays/s', 'cpu_baseline': nerf_cpu, 'parity': nerf_parity, 'reference_torch_gpu_mlp': torch_mlp, 'rays': 'NeRF convention (GetRays on random pixels of Blender spiral poses, radius 4), near 2 / far 6', 'workload': 'vanilla NeRF hierarchical 64 coarse + 192 fine evaluations per ray (configs[2]), 32768-ray batches, inference',
                     'ms_per_batch': float(nm.item()) / KN, 'roofline': {'bound': 'tensor', 'achieved': rps * flop_per_ray / 1e12 / world, 'peak': tpeak, 'unit': 'TFLOP/s',
                                                                          'frac': rps * flop_per_ray / 1e12 / world / tpeak, 'flop_per_ray': flop_per_ray,
                                                                          'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a multi-kernel step)'}}
