@@ -650,7 +650,12 @@ def run_ours(args):
                      'rays_per_step': world * N_RAYS, 'trained_rays_per_step': float(tsum.item()) / K, 'target_batch_size': T_TRAIN,
                      'compacted_samples_per_step_rank0': int(tr.compacted_samples().item()), 'grad_comm': tr.grad_comm, 'host_issue_ms_per_step': host_issue_ms, 'field_backward': 'tcgen05' if tr.bwd_impl == 1 else 'cuda cores',
                      'what': 'march + compaction (aux stream, one step ahead) | field fwd (tcgen05) + composite fwd + Huber x5 + composite bwd + field bwd (tcgen05 dX/dW) + gradient exchange '
-                             '(world>1: bf16 reduce-scatter -> sharded Adam -> fp16 all-gather; MLP weights fp32 all-reduce) + fused Adam over 12.2M params + cell-image refresh'}
+                             '+ Adam (world>1, grad_comm=peer: ONE optimiser kernel over NVLink peer memory - every rank sums all ranks\' bf16 gradients for its 1/N of the table, runs Adam on it and '
+                             'stores the new fp16 values into every rank\'s working table, csrc/peer_adam.cu; grad_comm=sharded: NCCL bf16 reduce-scatter -> sharded Adam -> fp16 all-gather) + cell-image refresh'}
+            if tr.px is not None:
+                tr.px.check()                      # raises if a rank timed out inside the exchange kernels
+                train['peer_exchange'] = 'ok'
+                tr.close()
             del tr
         except Exception as e:   # an auxiliary arm must never take the headline line down
             import traceback
@@ -1074,7 +1079,7 @@ def main():
     ap.add_argument('--no-mip', dest='no_mip', action='store_true', help='skip the Mip-NeRF arm')
     ap.add_argument('--no-ref-gpu', dest='no_ref_gpu', action='store_true', help='skip the GPU reference leg (reference raymarch_cuda kernels built for sm_100a, BASELINE.md B4)')
     ap.add_argument('--path', default='auto', choices=['auto', 'chain', 'fused'], help='inference path of the headline/e2e numbers: 5-launch chain, single-launch fused kernel, or the faster of the two (both are always measured)')
-    ap.add_argument('--grad-comm', dest='grad_comm', default='sharded', choices=['sharded', 'allreduce'], help='gradient exchange of the training arm at world > 1')
+    ap.add_argument('--grad-comm', dest='grad_comm', default='auto', choices=['auto', 'peer', 'sharded', 'allreduce'], help='gradient exchange of the training arm at world > 1 (peer: one optimiser kernel over NVLink peer memory, csrc/peer_adam.cu; auto: peer where CUDA IPC works, else sharded NCCL)')
     ap.add_argument('--pipeline', type=int, default=4, help='ray batches in flight (CUDA streams); 1 = strictly sequential steps')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup

@@ -41,6 +41,25 @@ extern "C" {
 #define XRB_ACT_LOGISTIC 2
 #define XRB_ACT_EXPONENTIAL 3
 
+/* ---- data-parallel optimiser step over NVLink peer memory (csrc/peer_adam.cu). Replaces, for the Instant-NGP trainer, what the reference gets from torch DDP's gradient all-reduce +
+ * torch.optim.Adam on every rank (core/apis/train.py:28-36, hashnerf.py:32-52): one exchange block per rank (flags | bf16 table gradient | fp32 MLP gradients | fp16 working table),
+ * allocated with xrb_peer_alloc, its 64-byte IPC handle passed to the other processes by the caller (any transport), opened there with xrb_peer_open.
+ *   xrb_peer_publish_grads  my fp32 gradients -> my block, then ready[rank] = step in every block
+ *   xrb_peer_adam_step      waits for every rank's gradients, Adam on my slice [rank*per, rank*per+per) of the table from the SUM of all ranks' gradients (mean: / world), new fp16
+ *                           values stored into every rank's working table; both MLP groups updated identically on every rank; returns (in stream order) once every rank's slice
+ *                           has landed in my working table. `step` is a counter starting at 1 that every rank advances together; opt_step is Adam's bias-correction step.
+ * Hyper-parameters as xrb_adam_ema_step. A rank that does not show up within ~2 s makes the kernels give up: xrb_peer_status != 0 (no hang). */
+typedef struct { int world, rank; void *base[8]; size_t off_g16, off_gmlp, off_t16; int64_t n_table, per, n_mlp; } xrb_peer_layout;
+typedef struct { float *param; void *param_fp16; float *exp_avg, *exp_avg_sq, *ema; int64_t n, g_off; } xrb_peer_mlp_group;
+int xrb_peer_alloc(size_t bytes, void **ptr, void *ipc_handle64);
+int xrb_peer_open(const void *ipc_handle64, void **ptr);
+int xrb_peer_close(void *ptr);
+int xrb_peer_free(void *ptr);
+int xrb_peer_publish_grads(const xrb_peer_layout *layout, const float *grad_table, const float *grad_mlp, uint32_t step, void *stream);
+int xrb_peer_adam_step(const xrb_peer_layout *layout, float *master_slice, float *exp_avg_slice, float *exp_avg_sq_slice, float *ema_slice, const xrb_peer_mlp_group *mlp0,
+                       const xrb_peer_mlp_group *mlp1, float lr, float beta1, float beta2, float eps, float weight_decay, int opt_step, float ema_momentum, uint32_t step, void *stream);
+int xrb_peer_status(const void *own_block, uint32_t *status_host, void *stream);
+
 /* ABI version, bumped on any signature change; and the compute capability the library was built for (100). */
 int xrb_abi_version(void);
 int xrb_built_for_sm(void);

@@ -28,6 +28,17 @@ class NgpTable(C.Structure):
     _fields_ = [('table_fp16', C.c_void_p), ('cell_image', C.c_void_p), ('n_packed_levels', C.c_int)]
 
 
+class PeerLayout(C.Structure):
+    """xrb_peer_layout: the exchange blocks of all ranks as mapped in this process + the layout inside a block (include/xrnerf_b200.h)"""
+    _fields_ = [('world', C.c_int), ('rank', C.c_int), ('base', C.c_void_p * 8), ('off_g16', C.c_size_t), ('off_gmlp', C.c_size_t), ('off_t16', C.c_size_t),
+                ('n_table', C.c_int64), ('per', C.c_int64), ('n_mlp', C.c_int64)]
+
+
+class PeerMlpGroup(C.Structure):
+    """xrb_peer_mlp_group: one small parameter vector every rank updates identically"""
+    _fields_ = [('param', C.c_void_p), ('param_fp16', C.c_void_p), ('exp_avg', C.c_void_p), ('exp_avg_sq', C.c_void_p), ('ema', C.c_void_p), ('n', C.c_int64), ('g_off', C.c_int64)]
+
+
 P = C.c_void_p
 _i, _f, _u64, _i64, _sz = C.c_int, C.c_float, C.c_uint64, C.c_int64, C.c_size_t
 _cfg = C.POINTER(NgpConfig)
@@ -73,6 +84,13 @@ _SIGS = {
     'xrb_adam_ema_step': (_i, [P, P, P, P, P, _i64, _f, _f, _f, _f, _f, _i, _f, P, _f, P]),
     'xrb_adam_ema_step_bf16grad': (_i, [P, P, P, P, P, _i64, _f, _f, _f, _f, _f, _i, _f, P, _f, P]),
     'xrb_pack_bf16': (_i, [P, P, _i64, P]),
+    'xrb_peer_alloc': (_i, [_sz, C.POINTER(C.c_void_p), P]),
+    'xrb_peer_open': (_i, [P, C.POINTER(C.c_void_p)]),
+    'xrb_peer_close': (_i, [P]),
+    'xrb_peer_free': (_i, [P]),
+    'xrb_peer_publish_grads': (_i, [C.POINTER(PeerLayout), P, P, C.c_uint32, P]),
+    'xrb_peer_adam_step': (_i, [C.POINTER(PeerLayout), P, P, P, P, C.POINTER(PeerMlpGroup), C.POINTER(PeerMlpGroup), _f, _f, _f, _f, _f, _i, _f, C.c_uint32, P]),
+    'xrb_peer_status': (_i, [P, C.POINTER(C.c_uint32), P]),
     'xrb_ngp_huber5_grad': (_i, [P, P, _i64, _f, P, P, P]),
     'xrb_ngp_render_workspace': (_sz, [_i, _i]),
     'xrb_ngp_render_fused_workspace': (_sz, []),

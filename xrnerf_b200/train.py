@@ -101,6 +101,82 @@ class ShardedExchange:
         return full
 
 
+class _DevView:
+    """a raw device pointer as a __cuda_array_interface__ object (torch.as_tensor wraps it without copying)"""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {'shape': (int(n),), 'typestr': typestr, 'data': (int(ptr), False), 'version': 2}
+
+
+class PeerExchange:
+    """The optimiser step of the data-parallel NGP trainer as ONE exchange over NVLink peer memory (csrc/peer_adam.cu, include/xrnerf_b200.h xrb_peer_*): every rank owns an
+    exchange block (flags | bf16 table gradient | fp32 MLP gradients | fp16 working table) that every other process maps through CUDA IPC. `t16` is this rank's working table INSIDE
+    its block: the field reads it, the other ranks' optimiser kernels write their slices into it."""
+
+    def __init__(self, n_table, n_mlp, group, dev):
+        import torch.distributed as dist
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise _C.XrbError('peer exchange: at most 8 ranks (one NVSwitch domain)')
+        self.n_table, self.n_mlp = int(n_table), int(n_mlp)
+        self.begin, self.end, self.per, self.padded = shard_range(n_table, self.world, self.rank)
+        a16 = lambda x: (x + 15) // 16 * 16   # noqa: E731
+        self.off_g16 = 128
+        self.off_gmlp = a16(self.off_g16 + 2 * self.padded)
+        self.off_t16 = a16(self.off_gmlp + 4 * self.n_mlp)
+        self.bytes = a16(self.off_t16 + 2 * self.padded)
+        # every rank must reach the same verdict (all map everything, or all fall back): failures are gathered, never raised between two collectives
+        own, handle, err = _C.C.c_void_p(), (_C.C.c_char * 64)(), None
+        try:
+            _C.check(_C.lib.xrb_peer_alloc(self.bytes, _C.C.byref(own), handle), 'peer_alloc')
+        except _C.XrbError as e:
+            err = str(e)
+        self.own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, None if err else bytes(handle.raw), group=group)
+        self.opened = []
+        self.layout = _C.PeerLayout(self.world, self.rank, (_C.C.c_void_p * 8)(), self.off_g16, self.off_gmlp, self.off_t16, self.n_table, self.per, self.n_mlp)
+        if all(h is not None for h in handles):
+            for p in range(self.world):
+                if p == self.rank:
+                    self.layout.base[p] = self.own
+                    continue
+                ptr = _C.C.c_void_p()
+                try:
+                    _C.check(_C.lib.xrb_peer_open((_C.C.c_char * 64).from_buffer_copy(handles[p]), _C.C.byref(ptr)), f'peer_open(rank {p})')
+                except _C.XrbError as e:
+                    err = str(e)
+                    break
+                self.layout.base[p] = ptr.value
+                self.opened.append(ptr.value)
+        else:
+            err = err or 'another rank could not allocate its exchange block'
+        verdicts = [None] * self.world
+        dist.all_gather_object(verdicts, err, group=group)
+        if any(v is not None for v in verdicts):
+            self.close()
+            raise _C.XrbError('peer exchange unavailable: ' + '; '.join(f'rank {r}: {v}' for r, v in enumerate(verdicts) if v is not None))
+        self.t16 = torch.as_tensor(_DevView(self.own + self.off_t16, self.padded, '<f2'), device=dev)
+        self.step = 0
+        dist.barrier(group=group)       # every block is mapped everywhere before anyone signals
+
+    def check(self):
+        st = _C.C.c_uint32(0)
+        _C.check(_C.lib.xrb_peer_status(self.own, _C.C.byref(st), _C.stream()), 'peer_status')
+        if st.value:
+            raise _C.XrbError(f'peer exchange: a rank did not arrive within the kernel time-out (status {st.value}: 1 = gradients, 9 = updated slices)')
+
+    def close(self):
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        for p in getattr(self, 'opened', []):
+            _C.lib.xrb_peer_close(p)
+        self.opened = []
+        if getattr(self, 'own', None):
+            _C.lib.xrb_peer_free(self.own)
+        self.own = None
+
+
 def huber5_grad(rgb, target, delta=0.1):
     """d/d rgb of 5 * HuberLoss(rgb, target, 0.1, 'sum') (networks/utils/metrics.py:8-16, hashnerf.py:39-44) and the loss value (torch restatement of
     xrb_ngp_huber5_grad, kept for the CPU tests that pin it to the reference's own metrics.py)."""
@@ -140,7 +216,7 @@ class _Slot:
 class NgpTrainer:
     def __init__(self, field, bitfield, n_rays, target_batch_size=1 << 18, aabb=(0.0, 1.0), near=0.05, cone=1.0 / 256, rgb_act=2, dens_act=3,
                  lr=1e-2, betas=(0.9, 0.99), eps=1e-15, weight_decay=1e-6, samples_per_ray_budget=64, group=None, ema_momentum=None, ema_warm_up=100,
-                 grad_comm='sharded', bwd_impl=None):
+                 grad_comm='auto', bwd_impl=None):
         import torch.distributed as dist
         self.f, self.bitfield, self.n_rays, self.T = field, bitfield, n_rays, int(target_batch_size)
         self.aabb, self.near, self.cone, self.rgb_act, self.dens_act = aabb, near, cone, rgb_act, dens_act
@@ -156,7 +232,18 @@ class NgpTrainer:
             field.set_packed_levels(6)     # the cell image is rebuilt after every optimiser step: 35 us for 6 levels (27.6 MB) vs 88 us for 7
         field.refresh()
         n_hash = field.hash_params.numel()
-        self.ex = ShardedExchange(n_hash, group) if self.grad_comm == 'sharded' else None
+        if self.grad_comm not in ('none', 'auto', 'sharded', 'allreduce', 'peer'):
+            raise ValueError(f'grad_comm {grad_comm!r}: one of auto, peer, sharded, allreduce')
+        self.px = None
+        if self.grad_comm in ('auto', 'peer'):     # auto: the peer-memory exchange where CUDA IPC between the ranks works (one NVLink / NVSwitch domain), else NCCL reduce-scatter / all-gather
+            try:
+                self.px = PeerExchange(field.hash_params.numel(), field.density_params.numel() + field.color_params.numel(), group, dev)
+                self.grad_comm = 'peer'
+            except _C.XrbError:
+                if self.grad_comm == 'peer':
+                    raise
+                self.grad_comm = 'sharded'
+        self.ex = ShardedExchange(n_hash, group) if self.grad_comm in ('sharded', 'peer') else None   # peer mode: slice bounds + the rare whole-tensor gathers (state_dict, EMA)
         pad = self.ex.padded if self.ex else n_hash
         # flat fp32 gradient: [hash (padded to the collective's size) | density | colour]
         self.gflat = torch.zeros(pad + field.density_params.numel() + field.color_params.numel(), dtype=torch.float32, device=dev)
@@ -165,13 +252,16 @@ class NgpTrainer:
         self.g_dens = self.g_mlp[:field.density_params.numel()]
         self.g_color = self.g_mlp[field.density_params.numel():]
         self.grads = [self.g_hash, self.g_dens, self.g_color]
+        if self.px is not None:
+            self._alias_table()
         if self.ex:
-            self.g16 = torch.zeros(pad, dtype=torch.bfloat16, device=dev)                 # wire format of the hash gradient
-            self.g16_mine = torch.zeros(self.ex.per, dtype=torch.bfloat16, device=dev)
+            if self.px is None:
+                self.g16 = torch.zeros(pad, dtype=torch.bfloat16, device=dev)                 # wire format of the hash gradient
+                self.g16_mine = torch.zeros(self.ex.per, dtype=torch.bfloat16, device=dev)
             b, e = self.ex.begin, self.ex.end
             self.m = [torch.zeros(e - b, device=dev), torch.zeros_like(field.density_params), torch.zeros_like(field.color_params)]
             self.v = [torch.zeros(e - b, device=dev), torch.zeros_like(field.density_params), torch.zeros_like(field.color_params)]
-            self.t16_pad = torch.zeros(pad, dtype=torch.float16, device=dev)               # all-gather target (padded copy of the fp16 table)
+            self.t16_pad = torch.zeros(pad, dtype=torch.float16, device=dev) if self.px is None else None   # all-gather target (padded copy of the fp16 table)
         else:
             self.m = [torch.zeros_like(p) for p in self.params]
             self.v = [torch.zeros_like(p) for p in self.params]
@@ -272,9 +362,52 @@ class NgpTrainer:
         _C.check(fn(_C.ptr(p), _C.ptr(p16), _C.ptr(g), _C.ptr(m), _C.ptr(v), p.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.step_n, div, _C.ptr(e), mom,
                     _C.stream()), 'adam')
 
+    def close(self):
+        """peer mode: give the field an ordinary fp16 table again (a copy of the working table) and release the exchange block and the mappings of the other ranks' blocks.
+        Collective in effect: every rank must stop stepping before any rank closes (the others write into this block)."""
+        if self.px is None:
+            return
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+        f = self.f
+        if f._table16 is not None and f._table16.data_ptr() == self.px.own + self.px.off_t16:
+            f._table16 = f._table16.clone()
+            f.tab = _C.NgpTable(f._table16.data_ptr(), f._cells.data_ptr() if f._cells is not None else None, f.n_packed if f._cells is not None else 0)
+        self.px.close()
+        self.px = None
+        self.grad_comm = 'closed'
+
+    def _alias_table(self):
+        """peer mode: the field's fp16 working table lives inside this rank's exchange block (the other ranks write their slices into it)"""
+        f, px = self.f, self.px
+        want = px.own + px.off_t16
+        if f._table16 is None or f._table16.data_ptr() != want:
+            if f._table16 is not None:
+                px.t16[:px.n_table].copy_(f._table16)
+            f._table16 = px.t16[:px.n_table]
+            f.tab = _C.NgpTable(want, f._cells.data_ptr() if f._cells is not None else None, f.n_packed if f._cells is not None else 0)
+
     def _exchange_and_update(self, mom):
         import torch.distributed as dist
         f = self.f
+        if self.grad_comm == 'peer':
+            px, ex, C = self.px, self.ex, _C.C
+            self._alias_table()
+            px.step += 1
+            st = _C.stream()
+            _C.check(_C.lib.xrb_peer_publish_grads(C.byref(px.layout), _C.ptr(self.g_hash), _C.ptr(self.g_mlp), px.step, st), 'peer_publish_grads')
+            nd = f.density_params.numel()
+            groups = [_C.PeerMlpGroup(_C.ptr(p.data), _C.ptr(p16), _C.ptr(m), _C.ptr(v), _C.ptr(e) if e is not None else None, p.numel(), off)
+                      for p, p16, m, v, e, off in ((f.density_params, f._dens16, self.m[1], self.v[1], self.ema[1], 0), (f.color_params, f._color16, self.m[2], self.v[2], self.ema[2], nd))]
+            b, e_ = ex.begin, ex.end
+            sl = f.hash_params.data[b:e_]
+            _C.check(_C.lib.xrb_peer_adam_step(C.byref(px.layout), _C.ptr(sl) if e_ > b else None, _C.ptr(self.m[0]) if e_ > b else None, _C.ptr(self.v[0]) if e_ > b else None,
+                                               _C.ptr(self.ema[0]) if (self.ema[0] is not None and e_ > b) else None, C.byref(groups[0]), C.byref(groups[1]), self.lr, self.betas[0],
+                                               self.betas[1], self.eps, self.wd, self.step_n, mom if self.ema[0] is not None else 0.0, px.step, st), 'peer_adam_step')
+            self.master_stale = True
+            return
         if self.grad_comm == 'sharded':
             ex = self.ex
             _C.check(_C.lib.xrb_pack_bf16(_C.ptr(self.gflat[:ex.padded]), _C.ptr(self.g16), ex.padded, _C.stream()), 'pack_bf16')
@@ -309,7 +442,7 @@ class NgpTrainer:
 
     def sync_master(self):
         """sharded mode: fetch the other ranks' slices of the fp32 master table (and EMA) so that state_dict() / EMA swaps see whole tensors"""
-        if self.grad_comm != 'sharded' or not self.master_stale:
+        if self.grad_comm not in ('sharded', 'peer') or not self.master_stale:
             return
         ex, f = self.ex, self.f
         full = torch.zeros(ex.padded, dtype=torch.float32, device=self.dev)
@@ -323,7 +456,7 @@ class NgpTrainer:
         """EMA of the hash table as one tensor (sharded mode gathers the slices)"""
         if self.ema[0] is None:
             return None
-        if self.grad_comm != 'sharded':
+        if self.grad_comm not in ('sharded', 'peer'):
             return self.ema[0]
         ex = self.ex
         full = torch.zeros(ex.padded, dtype=torch.float32, device=self.dev)
