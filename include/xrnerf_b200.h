@@ -48,7 +48,7 @@ extern "C" {
  *   xrb_peer_adam_step      waits for every rank's gradients, Adam on my slice [rank*per, rank*per+per) of the table from the SUM of all ranks' gradients (mean: / world), new fp16
  *                           values stored into every rank's working table; both MLP groups updated identically on every rank; returns (in stream order) once every rank's slice
  *                           has landed in my working table. `step` is a counter starting at 1 that every rank advances together; opt_step is Adam's bias-correction step.
- * Hyper-parameters as xrb_adam_ema_step. A rank that does not show up within ~2 s makes the kernels give up: xrb_peer_status != 0 (no hang). */
+ * Hyper-parameters as xrb_adam_ema_step. A rank that does not show up within ~10 s makes the kernels give up: xrb_peer_status != 0 (no hang). */
 typedef struct { int world, rank; void *base[8]; size_t off_g16, off_gmlp, off_t16; int64_t n_table, per, n_mlp; } xrb_peer_layout;
 typedef struct { float *param; void *param_fp16; float *exp_avg, *exp_avg_sq, *ema; int64_t n, g_off; } xrb_peer_mlp_group;
 int xrb_peer_alloc(size_t bytes, void **ptr, void *ipc_handle64);

@@ -12,7 +12,7 @@
 //                         the last CTA raises done[me] = step everywhere
 //   wait_done (1 kernel)  waits for done[*] == step: my t16 now holds every rank's slice, and nobody reads my g16 any more (it may be overwritten by the next step)
 // NVLink bytes per rank and step: (N-1)/N x 12.2 M x (2 + 2) B - what reduce-scatter + all-gather move - with no collective launch. Waits poll LOCAL memory.
-// A wait that lasts longer than ~2 s sets status != 0 in the block (read by xrb_peer_status) instead of hanging the GPU.
+// A wait that lasts longer than ~10 s sets status != 0 in the block (read by xrb_peer_status) instead of hanging the GPU.
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -23,7 +23,7 @@
 namespace xrb {
 
 constexpr int PEER_MAX = 8;
-constexpr long long PEER_SPIN_LIMIT = 4000000000ll;   // cycles (~2 s)
+constexpr long long PEER_SPIN_LIMIT = 20000000000ll;   // cycles (~10 s)
 // flags (uint32) at the start of a block: ready[8], done[8], ticket[2], status
 constexpr int F_READY = 0, F_DONE = 8, F_TICKET = 16, F_STATUS = 18;
 
@@ -51,7 +51,7 @@ __device__ __forceinline__ void peer_signal_when_all_ctas_done(const PeerDev &P,
         }
     }
 }
-// thread 0 polls MY flags until every rank's flag[slot + p] reached step; the CTA then proceeds. false (and status set) after ~2 s.
+// thread 0 polls MY flags until every rank's flag[slot + p] reached step; the CTA then proceeds. false (and status set) after ~10 s.
 __device__ __forceinline__ bool peer_wait_all(const PeerDev &P, int slot, uint32_t step) {
     __shared__ int ok;
     if (threadIdx.x == 0) {

@@ -395,6 +395,9 @@ class NgpTrainer:
         if self.grad_comm == 'peer':
             px, ex, C = self.px, self.ex, _C.C
             self._alias_table()
+            if px.step == 0:                 # first exchange: line the ranks up on the host once (lazy module loading / allocator warm-up differ by rank; the kernels give up after ~10 s)
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)
             px.step += 1
             st = _C.stream()
             _C.check(_C.lib.xrb_peer_publish_grads(C.byref(px.layout), _C.ptr(self.g_hash), _C.ptr(self.g_mlp), px.step, st), 'peer_publish_grads')
