@@ -345,7 +345,9 @@ int launch_field(const xrb_ngp_config *cfg, const xrb_ngp_table *tab, const void
         uint32_t image_bytes = weight_image_layout(cfg->density_hidden, cfg->color_hidden).total;
         // kernel shape (see ngp_field_tc_kernel): XRB_TC_SHAPE = 1 <2 WG,128 regs> (default: more gather loads in flight per thread; 154 us against 178 us per 699 K samples
         // isolated, 272 M against 260 M rays/s with four batches in flight although no register is left for another batch's march kernel to co-reside), 0 <2,96>, 2 <6,80>, 3 <8,64>
-        static const int shape = getenv("XRB_TC_SHAPE") ? atoi(getenv("XRB_TC_SHAPE")) : 1;
+        static const int env_shape = getenv("XRB_TC_SHAPE") ? atoi(getenv("XRB_TC_SHAPE")) : -1;
+        // impl 2 = the tensor-core kernel in its 96-register shape: 16 K registers per SM stay free, so a kernel of ANOTHER stream (the trainer's march of the next step) can run beside it
+        const int shape = env_shape >= 0 ? env_shape : (impl == 2 ? 0 : 1);
         static const int dbg = getenv("XRB_FIELD_DBG") ? atoi(getenv("XRB_FIELD_DBG")) : 0;
         // shape 4: the producer/consumer kernel (ngp_fused.cu in FIELD-ONLY mode): gather warps and tensor-core warpgroups are different warps
         if (shape == 4 && !density_only && (((uintptr_t)out) & 15) == 0) return launch_field_ps(cfg, g, tab, image, pts, pts_stride, dirs, dirs_stride, n, n_dev, out, s);

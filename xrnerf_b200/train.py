@@ -22,6 +22,8 @@ the other ranks are fetched on demand (`sync_master()`: checkpointing, validatio
 `grad_comm='allreduce'` keeps the dense fp32 all-reduce of round 1. The march of step k+1 runs on the aux stream while step k's exchange is in flight.
 The occupancy grid is updated identically on every rank (same weights + same RNG call index => same grid), so it needs no communication.
 """
+import os
+
 import torch
 
 from . import _C
@@ -227,6 +229,7 @@ class NgpTrainer:
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.grad_comm = grad_comm if self.world > 1 else 'none'
         self.bwd_impl = (1 if field.tc_backward_ok() else 0) if bwd_impl is None else bwd_impl
+        self.fwd_impl = int(os.environ.get('XRB_TRAIN_FWD_IMPL', '2'))   # 2: the 96-register shape of the field kernel, beside which the aux stream's march of the next batch fits on the SMs
         self.params = [field.hash_params, field.density_params, field.color_params]
         if field.n_packed > 6:
             field.set_packed_levels(6)     # the cell image is rebuilt after every optimiser step: 35 us for 6 levels (27.6 MB) vs 88 us for 7
@@ -330,7 +333,7 @@ class NgpTrainer:
         st = _C.stream()
         n_rows_dev = _C.ptr(s.cnt_c[1:2])
         pp, dp = _C.rows(s.coords_c[:, :3])[0], _C.rows(s.coords_c[:, 4:])[0]
-        _C.check(_C.lib.xrb_ngp_mlp_forward(f.cfg, f.tab, _C.ptr(f._dens16), _C.ptr(f._color16), _C.ptr(f._image), pp, 7, dp, 7, self.T, n_rows_dev, _C.ptr(self.raw), 1, st), 'field fwd')
+        _C.check(_C.lib.xrb_ngp_mlp_forward(f.cfg, f.tab, _C.ptr(f._dens16), _C.ptr(f._color16), _C.ptr(f._image), pp, 7, dp, 7, self.T, n_rows_dev, _C.ptr(self.raw), self.fwd_impl, st), 'field fwd')
         _C.check(_C.lib.xrb_rm_calc_rgb_forward(_C.ptr(self.raw), _C.ptr(s.coords_c), _C.ptr(s.numsteps), _C.ptr(s.numsteps_c), _C.f32(bg), self.n_rays, self.rgb_act, self.dens_act,
                                                 _C.ptr(self.rgb), st), 'calc_rgb_forward')
         self.loss_accum.zero_()
