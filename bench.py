@@ -1003,7 +1003,7 @@ def run_ours(args):
                 parity[path] = {'max_abs_rgb_err': float(err.max()), 'psnr_vs_ref_db': float(-10.0 * np.log10(max(mse, 1e-20))), 'sample_counts_bit_exact': bool(np.array_equal(ns_g, ns_cpu))}
         # L2 -> SM sector traffic of ONE field launch at this workload, from the committed ncu --set full capture (profiles/r02_ngp_field_tc_ncu_final.md: lts__t_sectors_srcunit_tex_op_read.sum
         # = 30.29 M sectors for 699 K samples = 43.3 sectors per sample): scaled to this run's sample count. DRAM traffic of the same capture: 47.15 MB read + 4.88 MB written.
-        SECTORS_PER_SAMPLE = 30169265 / 699287
+        SECTORS_PER_SAMPLE = 28552658 / 699287
         l2_bytes = iso_samples * SECTORS_PER_SAMPLE * 32
         l2_obj = None
         if l2_roof and 'error' not in l2_roof:
@@ -1043,8 +1043,8 @@ def run_ours(args):
                     'ms_per_step': e2e_ms / K, 'host_wall_ms_per_step': e2e_wall_ms / K},
             'gpu_launches': head['gpu_launches_per_step'] * K,
             # traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel at this workload, QUOTED from the committed ncu --set full capture of this
-            # round (profiles/r02_ngp_field_tc_ncu_final.md: 47.13 MB + 3.29 MB; fused kernel: profiles/r01b_ngp_render_fused_ncu.md 27.80 MB + 0.04 MB), not measured by this run
-            'roofline': dict(head['roofline'], traffic=(27.80e6 + 0.04e6) if use_fused else (47.13e6 + 3.29e6), traffic_source='quoted from the ncu --set full capture committed under profiles/ (bytes per launch); not measured by this run',
+            # round (profiles/r02_ngp_field_tc_ncu_final.md: 47.13 MB + 3.21 MB; fused kernel: profiles/r01b_ngp_render_fused_ncu.md 27.80 MB + 0.04 MB), not measured by this run
+            'roofline': dict(head['roofline'], traffic=(27.80e6 + 0.04e6) if use_fused else (47.13e6 + 3.21e6), traffic_source='quoted from the ncu --set full capture committed under profiles/ (bytes per launch); not measured by this run',
                              peak_source=peak_src,
                              note='hash table (24.4 MB fp16) + cell image are L2-resident by design: DRAM traffic is far below the algorithmic bytes; the gather runs under the L2 sector rate '
                                   '(l2_gather_roofline: every 4-byte entry costs a 32-byte sector), not under the HBM copy peak this frac is quoted against'),

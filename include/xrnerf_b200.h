@@ -189,8 +189,8 @@ int xrb_tcnn_mlp_backward(const void *params_fp16, const void *x_fp16, const voi
 
 /* HashNerfMLP.run_mlp (hashnerf_mlp.py:55-79) fused: pts/dirs f32 rows (stride in floats, so `coords[:, :3]` /
  * `coords[:, 4:]` views of a [S,7] buffer work in place) -> raw f32[n,4] = (rgb3, density1).
- * impl: 0 = SIMT (CUDA cores), 1 = tcgen05 tensor-core tiles (weights from `weight_image`), 2 = the same kernel in its 96-register shape (a quarter of the
- * register file stays free, so a kernel of another stream - the trainer's march of the next batch - can run beside it; ~15 % slower alone).
+ * impl: 0 = SIMT (CUDA cores), 1 (or 2) = tcgen05 tensor-core tiles (weights from `weight_image`); the kernel keeps a quarter of the register file free so that a
+ * kernel of another stream - the march of the next batch - can run beside it.
  * n_rows_dev (optional, device pointer): the effective row count is min(n, *n_rows_dev) — a sample count produced on the device by the
  * march / compaction never has to visit the host. */
 int xrb_ngp_mlp_forward(const xrb_ngp_config *cfg, const xrb_ngp_table *table, const void *density_fp16, const void *color_fp16,

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(128) mlp_forward_simt_kernel(const __half *__r
 // The gather is latency-bound (ncu: 69 % of the stall samples are long-scoreboard, issue 32 %, L1 65 %, L2 45 %), so the shapes trade registers per
 // thread for warps per SM:   <2,96> / <2,128>: two CTAs per SM (16 warps);  <6,80>: one CTA per SM, 24 warps;  <8,64>: one CTA per SM, 32 warps.
 // NP: static gather plan (ngp_field.cuh plan_mode): 0 = per-level form decided at run time, >0 = levels [0,NP) from the cell image, the rest hashed.
-// dbg (developer ablation, XRB_FIELD_DBG): 1 = no gather (encoding := position bits), 2 = no MLP layers.
+// dbg (developer ablation, XRB_FIELD_DBG): 1 = no gather (encoding := position bits), 2 = no MLP layers, 4 = plain per-tile loop (gather, then MLP) instead of the gather-ahead pipeline.
 template <bool DENSITY_ONLY, int NWG, int MAXREG, int NP>
 __global__ void __launch_bounds__(128 * NWG, NWG == 2 ? 2 : 1) __maxnreg__(MAXREG)
 ngp_field_tc_kernel(HashGridDev g, const __half2 *__restrict__ table, const uint8_t *__restrict__ cells, const void *__restrict__ weight_image, uint32_t image_bytes, int density_hidden,
@@ -175,6 +175,41 @@ ngp_field_tc_kernel(HashGridDev g, const __half2 *__restrict__ table, const uint
     const uint32_t tmem_base = c.tmem - c.wg * 64;
     const WeightImageLayout L = weight_image_layout(density_hidden, color_hidden);
     const int n_tiles = (n + 127) / 128;
+    if (!(dbg & 7)) {
+        // gather-ahead pipeline (dbg bit 2 = 4 selects the plain loop below): tile t+1's hash gather runs inside the waits of tile t's tensor-core layers
+        const int stride = gridDim.x * NWG;
+        int tile = blockIdx.x * NWG + c.wg;
+        if (tile < n_tiles) {
+            uint32_t e[16];
+            float dx = 0.5f, dy = 0.5f, dz = 0.5f;
+            {
+                const int i = tile * 128 + c.row;
+                float x = 0.5f, y = 0.5f, z = 0.5f;
+                if (i < n) {
+                    const float *p = pts + (size_t)i * pts_stride; x = p[0]; y = p[1]; z = p[2];
+                    if (!DENSITY_ONLY) { const float *d = dirs + (size_t)i * dirs_stride; dx = d[0]; dy = d[1]; dz = d[2]; }
+                }
+                tc_gather_levels<NP, 0, 16>(table, cells, g, x, y, z, e);
+            }
+            for (; tile < n_tiles; tile += stride) {
+                const int i = tile * 128 + c.row, in = i + stride * 128;
+                const bool has_next = tile + stride < n_tiles;
+                float xn = 0.5f, yn = 0.5f, zn = 0.5f, dxn = 0.5f, dyn = 0.5f, dzn = 0.5f;
+                if (has_next && in < n) {
+                    const float *p = pts + (size_t)in * pts_stride; xn = p[0]; yn = p[1]; zn = p[2];
+                    if (!DENSITY_ONLY) { const float *d = dirs + (size_t)in * dirs_stride; dxn = d[0]; dyn = d[1]; dzn = d[2]; }
+                }
+                uint32_t en[16];
+                const float4 raw = tc_field_gather_ahead<NP, DENSITY_ONLY>(c, L, density_hidden, color_hidden, table, cells, g, e, dx, dy, dz, has_next, xn, yn, zn, en);
+                if (i < n) { if (DENSITY_ONLY) out[i] = raw.x; else reinterpret_cast<float4 *>(out)[i] = raw; }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) e[k] = en[k];
+                dx = dxn; dy = dyn; dz = dzn;
+            }
+        }
+        tc_cta_teardown<TMEM_COLS>(tmem_base);
+        return;
+    }
     for (int tile = blockIdx.x * NWG + c.wg; tile < n_tiles; tile += gridDim.x * NWG) {
         const int i = tile * 128 + c.row;
         const bool valid = i < n;
@@ -343,11 +378,11 @@ int launch_field(const xrb_ngp_config *cfg, const xrb_ngp_table *tab, const void
                                                                  dirs, dirs_stride, n, n_dev, out);
     } else {
         uint32_t image_bytes = weight_image_layout(cfg->density_hidden, cfg->color_hidden).total;
-        // kernel shape (see ngp_field_tc_kernel): XRB_TC_SHAPE = 1 <2 WG,128 regs> (default: more gather loads in flight per thread; 154 us against 178 us per 699 K samples
-        // isolated, 272 M against 260 M rays/s with four batches in flight although no register is left for another batch's march kernel to co-reside), 0 <2,96>, 2 <6,80>, 3 <8,64>
+        // kernel shape (see ngp_field_tc_kernel): XRB_TC_SHAPE = 0 <2 WG, 96 regs> (default), 1 <2,128>, 2 <6,80>, 3 <8,64>. With the gather-ahead loop the two 2-warpgroup shapes
+        // are within 3 % of each other alone (151.6 vs 148.0 us per 699 K samples; before it 178 vs 154), and the 96-register one leaves 16 K registers per SM for a kernel
+        // of another stream - the march of the next batch - to run beside it: 276 vs 264-270 M rays/s with four batches in flight, 1.207 vs 1.27 ms per training step.
         static const int env_shape = getenv("XRB_TC_SHAPE") ? atoi(getenv("XRB_TC_SHAPE")) : -1;
-        // impl 2 = the tensor-core kernel in its 96-register shape: 16 K registers per SM stay free, so a kernel of ANOTHER stream (the trainer's march of the next step) can run beside it
-        const int shape = env_shape >= 0 ? env_shape : (impl == 2 ? 0 : 1);
+        const int shape = env_shape >= 0 ? env_shape : 0;   // (impl 2 is kept as a synonym of impl 1 for callers that asked for the co-residency shape explicitly)
         static const int dbg = getenv("XRB_FIELD_DBG") ? atoi(getenv("XRB_FIELD_DBG")) : 0;
         // shape 4: the producer/consumer kernel (ngp_fused.cu in FIELD-ONLY mode): gather warps and tensor-core warpgroups are different warps
         if (shape == 4 && !density_only && (((uintptr_t)out) & 15) == 0) return launch_field_ps(cfg, g, tab, image, pts, pts_stride, dirs, dirs_stride, n, n_dev, out, s);

@@ -33,9 +33,9 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 }
 __device__ __forceinline__ void a_store_chunk(const TcWarpgroup &c, uint32_t chunk, uint4 v) { *reinterpret_cast<uint4 *>(c.A + sw128_offset(c.row, chunk)) = v; }
 
-// D[128 x N] = A[128 x K] * W[N x K]^T
+// D[128 x N] = A[128 x K] * W[N x K]^T, in two halves so that a caller can put independent work (the NEXT tile's hash gather) between the issue and the wait
 template <int K, int N>
-__device__ __forceinline__ void tc_layer(TcWarpgroup &c, uint32_t w_off) {
+__device__ __forceinline__ void tc_layer_issue(TcWarpgroup &c, uint32_t w_off) {
     tc::fence_proxy_async_smem();   // my st.shared of the A row -> visible to the tensor-core (async) proxy
     tc::tc_fence_before_sync();     // my tcgen05.ld of the previous accumulator is ordered before the barrier
     tc::named_bar_sync(1 + c.wg, 128);
@@ -47,9 +47,16 @@ __device__ __forceinline__ void tc_layer(TcWarpgroup &c, uint32_t w_off) {
         for (int k = 0; k < K / 16; ++k) tc::mma_f16_ss(c.tmem, tc::smem_desc_sw128(a0 + k * 32), tc::smem_desc_sw128(b0 + k * 32), idesc, k > 0 ? 1u : 0u);
         tc::mma_commit(c.mbar);
     }
+}
+__device__ __forceinline__ void tc_layer_wait(TcWarpgroup &c) {
     tc::mbar_wait(c.mbar, c.phase);
     c.phase ^= 1u;
     tc::tc_fence_after_sync();
+}
+template <int K, int N>
+__device__ __forceinline__ void tc_layer(TcWarpgroup &c, uint32_t w_off) {
+    tc_layer_issue<K, N>(c, w_off);
+    tc_layer_wait(c);
 }
 
 // accumulator (64 fp32 columns of my lane) -> fp16 -> ReLU -> my A row (8 chunks). Rounding to fp16 first and clamping the packed pair
@@ -133,6 +140,71 @@ __device__ __forceinline__ float4 tc_field(TcWarpgroup &c, const WeightImageLayo
     float dout[16];
     tc_density<NP>(c, L, density_hidden, table, cells, g, x, y, z, dout);
     return tc_color_from_density(c, L, color_hidden, dout, dx, dy, dz);
+}
+
+// levels [L0, L1) of the hash encoding of one sample as packed half2 words
+template <int NP, int L0, int L1>
+__device__ __forceinline__ void tc_gather_levels(const __half2 *__restrict__ table, const uint8_t *__restrict__ cells, const HashGridDev &g, float x, float y, float z, uint32_t *e) {
+#pragma unroll
+    for (int l = L0; l < L1; ++l) { const float2 f = hash_level(table, cells, g, l, x, y, z, plan_mode<NP>(l)); e[l] = pack_h2(f.x, f.y); }
+}
+// One tile of the field with the NEXT tile's gather folded into the waits of this tile's five tensor-core layers (the layers of a tile are a chain of ~500-cycle
+// issue -> commit -> mbarrier round trips during which this warpgroup used to load nothing: ablation gather-only 132 us + MLP-only 48 us = 165 us for the whole kernel).
+//   e  : encoding of THIS tile's sample (16 packed half2), already gathered
+//   en : receives the encoding of the next tile's sample at (xn, yn, zn) when has_next
+// Same arithmetic, same order per sample: bit-identical to tc_density / tc_color_from_density.
+template <int NP, bool DENSITY_ONLY>
+__device__ __forceinline__ float4 tc_field_gather_ahead(TcWarpgroup &c, const WeightImageLayout &L, int density_hidden, int color_hidden, const __half2 *__restrict__ table,
+                                                        const uint8_t *__restrict__ cells, const HashGridDev &g, const uint32_t *e, float dx, float dy, float dz, bool has_next, float xn, float yn,
+                                                        float zn, uint32_t *en) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a_store_chunk(c, q, make_uint4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]));
+    tc_layer_issue<32, 64>(c, L.d_in);
+    if (has_next) tc_gather_levels<NP, 0, 3>(table, cells, g, xn, yn, zn, en);
+    tc_layer_wait(c);
+    for (int h = 0; h < density_hidden - 1; ++h) { tc_epilogue_relu_to_a(c); tc_layer<64, 64>(c, L.d_hid[h]); }
+    tc_epilogue_relu_to_a(c);
+    tc_layer_issue<64, 16>(c, L.d_out);
+    if (has_next) tc_gather_levels<NP, 3, 6>(table, cells, g, xn, yn, zn, en);
+    tc_layer_wait(c);
+    float dout[16];
+    tc_read_out16(c, dout);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) dout[k] = round_h(dout[k]);
+    if (DENSITY_ONLY) {
+        if (has_next) tc_gather_levels<NP, 6, 16>(table, cells, g, xn, yn, zn, en);
+        return make_float4(dout[0], 0.f, 0.f, 0.f);
+    }
+    {
+        float sh[16];
+        sh4(dx, dy, dz, sh);
+        float cin[32];
+#pragma unroll
+        for (int k = 0; k < 15; ++k) cin[k] = dout[k + 1];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) cin[15 + k] = sh[k];
+        cin[31] = 1.0f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            a_store_chunk(c, q, make_uint4(pack_h2(cin[8 * q], cin[8 * q + 1]), pack_h2(cin[8 * q + 2], cin[8 * q + 3]), pack_h2(cin[8 * q + 4], cin[8 * q + 5]), pack_h2(cin[8 * q + 6], cin[8 * q + 7])));
+    }
+    tc_layer_issue<32, 64>(c, L.c_in);
+    if (has_next) tc_gather_levels<NP, 6, 9>(table, cells, g, xn, yn, zn, en);
+    tc_layer_wait(c);
+    for (int h = 0; h < color_hidden - 1; ++h) {
+        tc_epilogue_relu_to_a(c);
+        tc_layer_issue<64, 64>(c, L.c_hid[h]);
+        if (h == 0 && has_next) tc_gather_levels<NP, 9, 12>(table, cells, g, xn, yn, zn, en);
+        tc_layer_wait(c);
+    }
+    if (color_hidden < 2 && has_next) tc_gather_levels<NP, 9, 12>(table, cells, g, xn, yn, zn, en);
+    tc_epilogue_relu_to_a(c);
+    tc_layer_issue<64, 16>(c, L.c_out);
+    if (has_next) tc_gather_levels<NP, 12, 16>(table, cells, g, xn, yn, zn, en);
+    tc_layer_wait(c);
+    float cout[16];
+    tc_read_out16(c, cout);
+    return make_float4(round_h(cout[0]), round_h(cout[1]), round_h(cout[2]), dout[0]);
 }
 
 // ---- CTA-level setup shared by the kernels that use the warpgroup evaluator

@@ -229,7 +229,7 @@ class NgpTrainer:
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.grad_comm = grad_comm if self.world > 1 else 'none'
         self.bwd_impl = (1 if field.tc_backward_ok() else 0) if bwd_impl is None else bwd_impl
-        self.fwd_impl = int(os.environ.get('XRB_TRAIN_FWD_IMPL', '2'))   # 2: the 96-register shape of the field kernel, beside which the aux stream's march of the next batch fits on the SMs
+        self.fwd_impl = 1
         self.params = [field.hash_params, field.density_params, field.color_params]
         if field.n_packed > 6:
             field.set_packed_levels(6)     # the cell image is rebuilt after every optimiser step: 35 us for 6 levels (27.6 MB) vs 88 us for 7
