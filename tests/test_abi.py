@@ -62,6 +62,34 @@ def test_argument_validation_without_gpu():
     assert lib.xrb_nerf_enc_image_bytes(129, 63) == 2 * 2 * 16384 and lib.xrb_nerf_enc_image_bytes(129, 96) == 2 * 3 * 16384
 
 
+def test_peer_exchange_argument_validation_without_gpu():
+    """xrb_peer_* (csrc/peer_adam.cu): the exchange layout is validated before any CUDA call"""
+    from xrnerf_b200 import _C
+    lib = _C.lib
+    buf = (C.c_char * 4096)()
+    a = (C.addressof(buf) + 255) & ~255
+
+    def layout(world=2, rank=0, per=1024, n_table=2000, n_mlp=10, off_g16=128, off_gmlp=128 + 2 * 2048, off_t16=128 + 2 * 2048 + 48, base=(1, 1)):
+        L = _C.PeerLayout(world, rank, (C.c_void_p * 8)(), off_g16, off_gmlp, off_t16, n_table, per, n_mlp)
+        for p, b in enumerate(base):
+            L.base[p] = a if b else None
+        return L
+    g = C.c_void_p(a)
+    assert lib.xrb_peer_publish_grads(C.byref(layout(world=9)), g, g, 1, None) == -1 and b'world' in lib.xrb_last_error()
+    assert lib.xrb_peer_publish_grads(C.byref(layout(rank=2)), g, g, 1, None) == -1
+    assert lib.xrb_peer_publish_grads(C.byref(layout(per=1001)), g, g, 1, None) == -1 and b'multiple of 8' in lib.xrb_last_error()
+    assert lib.xrb_peer_publish_grads(C.byref(layout(n_table=5000)), g, g, 1, None) == -1                       # the slices do not cover the table
+    assert lib.xrb_peer_publish_grads(C.byref(layout(off_g16=64)), g, g, 1, None) == -1 and b'flags' in lib.xrb_last_error()
+    assert lib.xrb_peer_publish_grads(C.byref(layout(off_t16=128 + 2 * 2048 + 50)), g, g, 1, None) == -1       # not 16-byte aligned
+    assert lib.xrb_peer_publish_grads(C.byref(layout(base=(1, 0))), g, g, 1, None) == -1 and b'null block' in lib.xrb_last_error()
+    assert lib.xrb_peer_publish_grads(C.byref(layout()), g, g, 0, None) == -1 and b'step' in lib.xrb_last_error()     # steps count from 1
+    grp = _C.PeerMlpGroup(a, None, a, a, None, 8, 4)
+    assert lib.xrb_peer_adam_step(C.byref(layout()), g, g, g, None, C.byref(grp), C.byref(grp), C.c_float(1e-2), C.c_float(.9), C.c_float(.99), C.c_float(1e-15), C.c_float(0), 1, C.c_float(0), 1,
+                                  None) == -1 and b'outside the gradient block' in lib.xrb_last_error()          # g_off + n > n_mlp
+    assert lib.xrb_peer_alloc(64, None, None) == -1 and lib.xrb_peer_open(None, None) == -1
+    assert lib.xrb_peer_close(None) == 0 and lib.xrb_peer_free(None) == 0
+
+
 def test_strided_or_wrong_dtype_tensors_are_rejected():
     """Round-1 W1: a Fortran-ordered rays_o (what `broadcast_to -> reshape -> astype` + torch.from_numpy gives) was handed to the kernels as a bare
     data_ptr() and silently rendered different rays. Every dense-row pointer now goes through _C.ptr, which refuses non-contiguous / wrong-dtype
