@@ -168,7 +168,16 @@ class PeerExchange:
         if st.value:
             raise _C.XrbError(f'peer exchange: a rank did not arrive within the kernel time-out (status {st.value}: 1 = gradients, 9 = updated slices)')
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # noqa: BLE001  (interpreter shutdown)
+            pass
+
     def close(self):
+        """releases the mappings and this rank's block. `t16` (and anything aliasing it, e.g. a field's working table) must not be used afterwards: NgpTrainer.close() re-homes the table first."""
+        if not getattr(self, 'own', None) and not getattr(self, 'opened', None):
+            return
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         for p in getattr(self, 'opened', []):
