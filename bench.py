@@ -1080,7 +1080,7 @@ def main():
     ap.add_argument('--no-ref-gpu', dest='no_ref_gpu', action='store_true', help='skip the GPU reference leg (reference raymarch_cuda kernels built for sm_100a, BASELINE.md B4)')
     ap.add_argument('--path', default='auto', choices=['auto', 'chain', 'fused'], help='inference path of the headline/e2e numbers: 5-launch chain, single-launch fused kernel, or the faster of the two (both are always measured)')
     ap.add_argument('--grad-comm', dest='grad_comm', default='auto', choices=['auto', 'peer', 'sharded', 'allreduce'], help='gradient exchange of the training arm at world > 1 (peer: one optimiser kernel over NVLink peer memory, csrc/peer_adam.cu; auto: peer where CUDA IPC works, else sharded NCCL)')
-    ap.add_argument('--pipeline', type=int, default=4, help='ray batches in flight (CUDA streams); 1 = strictly sequential steps')
+    ap.add_argument('--pipeline', type=int, default=8, help='ray batches in flight (CUDA streams); 1 = strictly sequential steps. Measured on one B200: 2 -> 240, 4 -> 271, 6 -> 287, 8 -> 292 M rays/s')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
