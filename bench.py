@@ -15,7 +15,11 @@ A "step" is one pass of the hot path (ray march -> hash/SH encode -> tiny MLPs -
              + 16 B raw out per sample
   cpu_baseline / --impl reference   the reference's own ngp_raymarch kernels compiled for CPU (oracle/_ref) for march and
              compositing + the C restatement of tcnn (oracle port) for the field, all host cores, on a bounded ray sample.
-Multi-GPU (torchrun): rays shard over ranks with no data-path collective (weak scaling: 65 536 rays per rank per step).
+  reference_gpu / nerf.reference_torch_gpu_mlp   BASELINE.md B4 / B3: the reference's own CUDA kernels (built unmodified for sm_100a, oracle/build_ref_cuda.py) and its
+             NerfMLP arithmetic on cuBLAS, timed per op on this GPU next to ours (rank 0, N = 1)
+Steps are issued on `--pipeline` CUDA streams (default 8 batches in flight, each with its own workspace; stated in config.batches_in_flight): throughput, not latency.
+Multi-GPU (torchrun): rays shard over ranks with no data-path collective (weak scaling: 65 536 rays per rank per step); the training arm's optimiser exchange runs over
+NVLink peer memory (csrc/peer_adam.cu; --grad-comm).
 """
 import argparse
 import json
